@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- MSDA forward+backward throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port), rank 0 only
+    torchrun ... bench.py --gpus N ...                       # one rank per GPU (weak scaling by batch)
+
+One "step" = one MSDA forward + backward over one synthetic batch of the headline workload
+(BASELINE.json configs[1]: KITTI 384x1280 encoder self-attention, 4 levels 48x160..6x20,
+10200 queries, 8 heads x 32 channels, 4 points, batch 16, fp32).  The op is batch-local
+(SURVEY.md 8e): with N GPUs every rank runs its own batch of 16, no data-path collective.
+
+Printed JSON (rank 0, one line):
+  value      algorithmic GB moved per second, whole job, inputs resident in HBM
+             (algorithmic bytes: SURVEY.md 8d / monosowa_b200.workloads.algorithmic_bytes)
+  e2e        same metric through the public API (MSDeformAttnFunction.apply + autograd) with
+             pinned HOST buffers: H2D of value/loc/attn/grad_out and D2H of out + the three
+             gradients inside the timed region
+  roofline   dominant kernel (the backward scatter): algorithmic bytes / CUDA-event time vs the
+             measured HBM copy peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference's ms_deform_attn_core_pytorch on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MSDA fwd+bwd GB/s"
+UNIT = "GB/s"
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+# ------------------------------------------------------------------------------------------
+# helpers (importable by the CPU tests)
+# ------------------------------------------------------------------------------------------
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def aggregate(local_bytes_per_step: float, local_ms_per_step: float, world: int, reduce_fn=None):
+    """Whole-job throughput: all ranks' bytes / the slowest rank's time.  `reduce_fn(tensor, op)`
+    performs the all-reduce (None = single process)."""
+    t = torch.tensor([local_ms_per_step], dtype=torch.float64)
+    b = torch.tensor([local_bytes_per_step], dtype=torch.float64)
+    if reduce_fn is not None and world > 1:
+        t = reduce_fn(t, "max")
+        b = reduce_fn(b, "sum")
+    ms = float(t.item())
+    return float(b.item()) / (ms * 1e-3) / 1e9, ms
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.gpu = None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation (oracle port of ms_deform_attn_core_pytorch)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(wl, sample_batch):
+    """Returns (step, bytes_per_step, description).  The sample is `sample_batch` images of the
+    workload -- the grid_sample path materialises (N*M, D, Lq, L*P) and needs ~0.7 s/image-pair."""
+    from oracle import msda_oracle as O                      # checker used as the CPU baseline only
+    from monosowa_b200 import workloads as W
+    swl = W.config(1, batch=sample_batch, loc_mode=wl.loc_mode, seed=wl.seed)
+    d = W.make_inputs(swl, device="cpu")
+
+    def step():
+        O.core_grid_sample_fwd_bwd(d["value"], d["shapes"], d["loc"], d["attn"], d["grad_out"])
+
+    return step, W.algorithmic_bytes(swl)["total"], f"{sample_batch} of {wl.batch} images of {wl.name} per step"
+
+
+def time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    return statistics.mean(ts) * 1e3
+
+
+def run_reference_arm(args, wl):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, nbytes, sample = cpu_reference_step_fn(wl, sample_batch=2)
+    steps = max(1, min(args.steps, 8))
+    ms = time_cpu(step, steps, max(1, min(args.warmup, 2)))
+    val = nbytes / (ms * 1e-3) / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl, world),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+                         "what": "oracle.core_grid_sample (restated ms_deform_attn_core_pytorch, grid_sample) fwd + autograd bwd"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl, world):
+    return {"workload": f"BASELINE.json configs[1]: MSDA encoder self-attention fwd+bwd, KITTI 384x1280 "
+                        f"(levels {wl.shapes}), {wl.Lq} queries, {wl.heads} heads x {wl.head_dim}, {wl.points} points, "
+                        f"batch {wl.batch}/GPU, {str(wl.dtype).replace('torch.', '')}",
+            "name": wl.name, "batch_per_gpu": wl.batch, "global_batch": wl.batch * world, "queries": wl.Lq,
+            "loc_mode": wl.loc_mode, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
+            "l2_policy": "inputs (585 MB/step) exceed the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import monosowa_b200 as msda
+    from monosowa_b200 import workloads as W
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    d = W.make_inputs(wl, device=dev, seed=wl.seed + 1000 * rank)
+    ab = W.algorithmic_bytes(wl)
+    fwd_op, bwd_op = torch.ops.msda.forward, torch.ops.msda.backward
+    a5 = (d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"])
+
+    def step_device():
+        out = fwd_op(*a5, 64)
+        return out, bwd_op(*a5, d["grad_out"], 64)
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) + per-kernel events (roofline) ----------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    n0 = msda._lib.launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        ev[i][0].record()
+        out = fwd_op(*a5, 64)
+        ev[i][1].record()
+        grads = bwd_op(*a5, d["grad_out"], 64)
+        ev[i][2].record()
+    t_end.record()
+    barrier()
+    launches = msda._lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = t_start.elapsed_time(t_end) / args.steps
+    fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
+    bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
+
+    def reduce_fn(t, op):
+        tt = t.to(dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return tt.cpu()
+
+    value, ms_max = aggregate(ab["total"], ms_step, world, reduce_fn if use_dist else None)
+
+    # ---- end to end: pinned host buffers in, results back to pinned host buffers -------------
+    host_in = {k: d[k].cpu().pin_memory() for k in ("value", "loc", "attn", "grad_out")}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_in.values())
+    host_out = None
+    F = msda.MSDeformAttnFunction.apply
+    chunks = args.e2e_chunks if wl.batch % args.e2e_chunks == 0 else 1
+    cb = wl.batch // chunks
+    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+
+    def step_e2e():
+        nonlocal host_out
+        res = []
+        cur = torch.cuda.current_stream()
+        for s in (s_in, s_cmp, s_out):
+            s.wait_stream(cur)
+        for c in range(chunks):
+            sl = slice(c * cb, (c + 1) * cb)
+            with torch.cuda.stream(s_in):
+                dv = {k: host_in[k][sl].to(dev, non_blocking=True) for k in host_in}
+                e_in = torch.cuda.Event(); e_in.record()
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(e_in)
+                v = dv["value"].requires_grad_(True); l = dv["loc"].requires_grad_(True); a = dv["attn"].requires_grad_(True)
+                o = F(v, d["shapes"], d["lsi"], l, a, 64)
+                o.backward(dv["grad_out"])
+                e_c = torch.cuda.Event(); e_c.record()
+                for t in dv.values():
+                    t.record_stream(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e_c)
+                outs = (o.detach(), v.grad, l.grad, a.grad)
+                if host_out is None:
+                    host_out = [torch.empty((wl.batch,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory() for t in outs]
+                for h, t in zip(host_out, outs):
+                    h[sl].copy_(t, non_blocking=True)
+                    t.record_stream(s_out)
+            res.append(outs)
+        cur.wait_stream(s_out)
+        return res
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_e2e()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    d2h_bytes = sum(t.numel() * t.element_size() for t in host_out)
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    e2e_value, e2e_ms_max = aggregate(ab["total"], e2e_ms, world, reduce_fn if use_dist else None)
+    # sanity: the e2e path produced the same forward as the device path
+    chk = torch.equal(host_out[0].to(dev), out) if rank == 0 else True
+
+    if rank != 0:
+        if use_dist:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    dom = ("bwd", bwd_ms, ab["bwd"]) if bwd_ms >= fwd_ms else ("fwd", fwd_ms, ab["fwd"])
+    achieved = dom[2] / (dom[1] * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {torch.float32: "f32", torch.bfloat16: "bf16", torch.float64: "f64"}[wl.dtype], "data": "synthetic",
+        "config": workload_config(wl, world),
+        "frac_of_hbm_peak": value / world / peak,
+        "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+        "fwd_GBps": ab["fwd"] / (fwd_ms * 1e-3) / 1e9, "bwd_GBps": ab["bwd"] / (bwd_ms * 1e-3) / 1e9,
+        "algorithmic_bytes": {"fwd": ab["fwd"], "bwd": ab["bwd"], "gather_cache_level": ab["gather"]},
+        "kernels": {"fwd": msda._lib.lib.msda_describe_forward(32, 0, wl.head_dim, wl.L, wl.points).decode(),
+                    "bwd": msda._lib.lib.msda_describe_backward(32, 0, wl.head_dim, wl.L, wl.points).decode()},
+        "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": load_traffic(dom[0]), "peak_source": peak_src,
+                     "note": "achieved = algorithmic bytes of the launch / CUDA-event time on the launch stream; "
+                             "bwd includes its cudaMemsetAsync of grad_value"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_max, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "chunks": chunks, "matches_device_path": bool(chk),
+                "api": "MSDeformAttnFunction.apply + autograd, pinned host buffers, 3-stream pipeline"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "lib": msda._lib.build_info(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        step, nbytes, sample = cpu_reference_step_fn(wl, sample_batch=2)
+        ms = time_cpu(step, args.cpu_steps, 1)
+        line["cpu_baseline"] = {"value": nbytes / (ms * 1e-3) / 1e9, "unit": UNIT, "cores": torch.get_num_threads(),
+                                "kind": "port", "sample": sample + f", {args.cpu_steps} timed steps", "ms_per_step": ms}
+    if world == 1 and not args.no_ref_cuda:
+        line["ref_cuda_kernel"] = time_reference_cuda(d, ab, args)
+    print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def load_traffic(kernel):
+    """dram bytes per launch from the committed ncu capture, if one has been summarised."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def time_reference_cuda(d, ab, args):
+    """The reference's own CUDA kernels recompiled for sm_100a (oracle/_ref), same inputs, same
+    event timing -- the on-GPU baseline of BASELINE.md 2b.  Reported beside, never part of, `value`."""
+    try:
+        from oracle import msda_oracle as O
+        if not O.ref_cuda_available():
+            return {"unavailable": "oracle/_ref/libmsda_ref_sm100.so not built"}
+        a5 = (d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"])
+        for _ in range(2):
+            O.ref_cuda_forward(*a5); O.ref_cuda_backward(*a5, d["grad_out"])
+        n = max(3, min(args.steps, 10))
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        fw = bw = 0.0
+        for _ in range(n):
+            e[0].record(); O.ref_cuda_forward(*a5); e[1].record(); O.ref_cuda_backward(*a5, d["grad_out"]); e[2].record()
+            torch.cuda.synchronize()
+            fw += e[0].elapsed_time(e[1]); bw += e[1].elapsed_time(e[2])
+        fw, bw = fw / n, bw / n
+        return {"fwd_ms": fw, "bwd_ms": bw, "GBps": ab["total"] / ((fw + bw) * 1e-3) / 1e9,
+                "what": "reference ms_deform_im2col_cuda.cuh kernels, nvcc sm_100a, incl. their at::zeros-equivalent memsets"}
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": repr(exc)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--loc-mode", default="model", choices=["model", "uniform"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    from monosowa_b200 import workloads as W
+    wl = W.config(1, batch=args.batch, loc_mode=args.loc_mode)
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

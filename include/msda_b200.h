@@ -1,0 +1,123 @@
+/*
+ * msda_b200.h -- C ABI of libmsda_b200.so: MultiScaleDeformableAttention forward/backward
+ * for NVIDIA B200 (sm_100a).  Plain pointers and sizes only: no torch / ATen / pybind types.
+ *
+ * This is the drop-in boundary for the reference's compiled extension
+ * "MultiScaleDeformableAttention" (jskvrna/MonoSOWA, paths relative to
+ * MonoDETR/lib/models/monodetr/ops/):
+ *
+ *   msda_forward_*   replaces  ms_deform_attn_forward   src/ms_deform_attn.h:20-38
+ *                              -> ms_deform_attn_cuda_forward   src/cuda/ms_deform_attn_cuda.cu:20-80
+ *                              -> ms_deformable_im2col_cuda     src/cuda/ms_deform_im2col_cuda.cuh:923-954
+ *   msda_backward_*  replaces  ms_deform_attn_backward  src/ms_deform_attn.h:41-61
+ *                              -> ms_deform_attn_cuda_backward  src/cuda/ms_deform_attn_cuda.cu:83-153
+ *                              -> ms_deformable_col2im_cuda     src/cuda/ms_deform_im2col_cuda.cuh:956-1327
+ *   (Python binding that sat on top: PYBIND11_MODULE in src/vision.cpp:13-16, called from
+ *    functions/ms_deform_attn_func.py:25 and :35.)
+ *
+ * Differences from the reference boundary, all deliberate:
+ *   - the caller owns every buffer; the library never allocates or frees device memory
+ *     (the reference allocates outputs with at::zeros, ms_deform_attn_cuda.cu:54,121-123);
+ *   - the whole batch is processed by one launch -- the reference's im2col_step chunk loop
+ *     (ms_deform_attn_cuda.cu:61,131) is a host-side artefact with no numerical effect; the
+ *     Python layer still validates batch % min(batch, im2col_step) == 0 like :52 does;
+ *   - errors are returned, not printf'ed (the reference prints cudaGetLastError, cuh:948-952);
+ *   - a bf16 variant exists (the reference dispatches float/double only, .cu:64,134).
+ *
+ * Tensor layouts (all contiguous, row-major, device memory unless noted):
+ *   value            [N, S, M, D]          S = sum_l H_l*W_l
+ *   spatial_shapes   [L, 2]  int64 (H, W)  DEVICE memory (read inside the kernels)
+ *   level_start_index[L]     int64         DEVICE memory
+ *   sampling_loc     [N, Lq, M, L, P, 2]   normalised (x, y); may lie outside [0, 1]
+ *   attn_weight      [N, Lq, M, L, P]
+ *   out / grad_out   [N, Lq, M, D]
+ *   grad_value       like value; grad_loc like sampling_loc; grad_attn like attn_weight
+ * Semantics: pixel coordinate = loc * size - 0.5 (grid_sample align_corners=False), bilinear,
+ * zero padding per corner, samples outside (-1, size) skipped (cuh:285-291, 33-84).
+ *
+ * Every entry point enqueues work on `stream` (a cudaStream_t passed as void*; NULL = the
+ * legacy default stream) and returns immediately: no host synchronisation, no host reads of
+ * device metadata, safe inside CUDA-graph capture.  Return value: MSDA_OK, a negative
+ * MSDA_ERR_* argument error, or a positive cudaError_t from the launch.  After a non-zero
+ * return msda_last_error() (thread-local) describes it.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+#define MSDA_MAX_LEVELS 16
+
+enum {
+    MSDA_OK = 0,
+    MSDA_ERR_NULL_POINTER = -1, /* a required pointer is NULL (and the tensor is non-empty) */
+    MSDA_ERR_BAD_SHAPE = -2,    /* negative size, L > MSDA_MAX_LEVELS, or a size overflow   */
+    MSDA_ERR_MISALIGNED = -3,   /* a pointer is not aligned to its element size             */
+};
+
+/* ---- fp32: value/loc/attn/out all float ------------------------------------------------ */
+int msda_forward_f32(const void *value, const int64_t *spatial_shapes,
+                     const int64_t *level_start_index, const void *sampling_loc,
+                     const void *attn_weight, void *out,
+                     int N, int S, int M, int D, int L, int Lq, int P, void *stream);
+
+/* grad_value is zero-filled by the library on `stream` before the scatter. */
+int msda_backward_f32(const void *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start_index, const void *sampling_loc,
+                      const void *attn_weight, const void *grad_out,
+                      void *grad_value, void *grad_loc, void *grad_attn,
+                      int N, int S, int M, int D, int L, int Lq, int P, void *stream);
+
+/* ---- fp64: everything double (keeps the reference's gradcheck contract, ops/test.py:63-86) */
+int msda_forward_f64(const void *value, const int64_t *spatial_shapes,
+                     const int64_t *level_start_index, const void *sampling_loc,
+                     const void *attn_weight, void *out,
+                     int N, int S, int M, int D, int L, int Lq, int P, void *stream);
+
+int msda_backward_f64(const void *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start_index, const void *sampling_loc,
+                      const void *attn_weight, const void *grad_out,
+                      void *grad_value, void *grad_loc, void *grad_attn,
+                      int N, int S, int M, int D, int L, int Lq, int P, void *stream);
+
+/* ---- bf16: value / out / grad_out are bfloat16; sampling_loc, attn_weight, grad_loc and
+ *      grad_attn stay float (bf16 cannot hold sub-pixel coordinates); arithmetic is fp32.
+ *      grad_value_f32 is a FLOAT accumulation buffer shaped like value (zero-filled here);
+ *      the caller narrows it to bf16 once the scatter is complete. ------------------------ */
+int msda_forward_bf16(const void *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start_index, const void *sampling_loc,
+                      const void *attn_weight, void *out,
+                      int N, int S, int M, int D, int L, int Lq, int P, void *stream);
+
+int msda_backward_bf16(const void *value, const int64_t *spatial_shapes,
+                       const int64_t *level_start_index, const void *sampling_loc,
+                       const void *attn_weight, const void *grad_out,
+                       void *grad_value_f32, void *grad_loc, void *grad_attn,
+                       int N, int S, int M, int D, int L, int Lq, int P, void *stream);
+
+/* ---- introspection ---------------------------------------------------------------------- */
+int msda_abi_version(void);            /* == MSDA_ABI_VERSION                                */
+const char *msda_build_info(void);     /* "sm_100a nvcc <ver> <date>"                        */
+const char *msda_last_error(void);     /* thread-local; "" when the last call succeeded      */
+long long msda_launch_count(void);     /* kernels this library has launched so far (memsets excluded) */
+
+/* Kernel-selection knobs, for benchmarking A/B runs only (process-wide, not thread-safe
+ * against concurrent launches).  key: "fwd_variant", "bwd_variant", "block_threads".
+ * value -1 restores the default heuristic.  Returns MSDA_OK or MSDA_ERR_BAD_SHAPE (unknown key). */
+int msda_set_tuning(const char *key, int value);
+int msda_get_tuning(const char *key);
+
+/* Name of the kernel the current heuristics pick for this problem, e.g. "fwd_vec_f32_d32_p4"
+ * or "fwd_generic_f64" (static storage; for logs, tests and bench.py). */
+const char *msda_describe_forward(int dtype_bits, int is_bf16, int D, int L, int P);
+const char *msda_describe_backward(int dtype_bits, int is_bf16, int D, int L, int P);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

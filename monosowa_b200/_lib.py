@@ -1,0 +1,72 @@
+"""ctypes loader for libmsda_b200.so (C ABI in include/msda_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing and cannot be built,
+importing this module raises.  The product never routes through oracle/ or any CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmsda_b200.so")
+
+_vp, _i64p, _int = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int
+_FWD = [_vp, _i64p, _i64p, _vp, _vp, _vp] + [_int] * 7 + [_vp]
+_BWD = [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]
+
+EXPORTS = {
+    "msda_forward_f32": (_int, _FWD), "msda_forward_f64": (_int, _FWD), "msda_forward_bf16": (_int, _FWD),
+    "msda_backward_f32": (_int, _BWD), "msda_backward_f64": (_int, _BWD), "msda_backward_bf16": (_int, _BWD),
+    "msda_abi_version": (_int, []),
+    "msda_build_info": (ctypes.c_char_p, []),
+    "msda_last_error": (ctypes.c_char_p, []),
+    "msda_launch_count": (ctypes.c_longlong, []),
+    "msda_set_tuning": (_int, [ctypes.c_char_p, _int]),
+    "msda_get_tuning": (_int, [ctypes.c_char_p]),
+    "msda_describe_forward": (ctypes.c_char_p, [_int] * 5),
+    "msda_describe_backward": (ctypes.c_char_p, [_int] * 5),
+}
+ABI_VERSION = 1
+
+
+def _open() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as exc:  # noqa: BLE001
+            raise ImportError(
+                f"monosowa_b200: {LIB_PATH} is missing and could not be built ({exc}). "
+                "Run `python -m monosowa_b200.build`. There is no CPU or PyTorch fallback.") from exc
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)          # AttributeError here = ABI mismatch: fail loudly
+        fn.restype, fn.argtypes = res, args
+    if lib.msda_abi_version() != ABI_VERSION:
+        raise ImportError(f"monosowa_b200: ABI version {lib.msda_abi_version()} != expected {ABI_VERSION}; rebuild")
+    return lib
+
+
+lib = _open()
+
+
+def last_error() -> str:
+    return lib.msda_last_error().decode()
+
+
+def launch_count() -> int:
+    return int(lib.msda_launch_count())
+
+
+def set_tuning(key: str, value: int) -> None:
+    if lib.msda_set_tuning(key.encode(), int(value)) != 0:
+        raise ValueError(last_error())
+
+
+def get_tuning(key: str) -> int:
+    return int(lib.msda_get_tuning(key.encode()))
+
+
+def build_info() -> str:
+    return lib.msda_build_info().decode()

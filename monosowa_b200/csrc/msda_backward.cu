@@ -1,0 +1,305 @@
+// msda_backward.cu -- MSDA backward kernels for sm_100a.
+//
+// Replaces the reference's seven col2im kernels and their dispatcher (reference
+// MonoDETR/lib/models/monodetr/ops/src/cuda/ms_deform_im2col_cuda.cuh:301-920, 956-1327;
+// gradient formulas :87-159).  Machine mapping (see also msda_forward.cu):
+//   * a lane owns a 128-bit channel vector; D/VEC lanes form the lane group of one (query, head);
+//   * grad_value: one REDG.E.ADD.F32x4 (red.global.add.v4.f32) per lane per corner instead of
+//     four scalar atomicAdds -- the reference issues 4 scalar atomics per channel per sample;
+//   * grad_sampling_loc / grad_attn_weight: per-lane partial dot products are combined with a
+//     butterfly reduce-scatter over the lane group (warp shuffles only) and written once, fully
+//     overwriting the outputs -- no shared memory, no block barriers, no zero-fill needed
+//     (the reference: smem staging, 2 __syncthreads and a serial D-way sum per sample point);
+//   * level geometry is staged in shared memory once per CTA.
+#include "msda_common.cuh"
+
+namespace msda {
+
+template <typename VT, int D, int P>
+__global__ void __launch_bounds__(512)
+bwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
+               const int64_t *__restrict__ lsi, const float *__restrict__ loc,
+               const float *__restrict__ attn, const VT *__restrict__ grad_out,
+               float *__restrict__ grad_value, float *__restrict__ grad_loc,
+               float *__restrict__ grad_attn, const Dims d, const int order)
+{
+    constexpr int VEC = Vec<VT>::N;
+    constexpr int G = D / VEC;
+    constexpr int QPW = 32 / G;
+    static_assert(D % VEC == 0 && G >= 1 && G <= 32 && (32 % G) == 0, "unsupported D");
+
+    __shared__ LevelInfo s_lv[MSDA_MAX_LEVELS];
+    stage_levels(s_lv, shapes, lsi, d.L);
+
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    WorkItem w = decode_work<QPW>(d, order, lane / G);
+    // warps are all-or-nothing past the end of the problem; inside a live warp, lane groups
+    // beyond Lq keep running (they take part in the shuffles) with every sample masked off.
+    if (__ballot_sync(kFullMask, w.valid) == 0) return;
+    if (!w.valid) { w.n = 0; w.q = 0; w.m = 0; }
+
+    const long qm = ((long)w.n * d.Lq + w.q) * d.M + w.m;
+    const long img = ((long)w.n * d.S * d.M + w.m) * D + gl * VEC;
+    const VT *vimg = value + img;
+    float *gvimg = grad_value + img;
+    const float *lp = loc + qm * (long)(d.L * P * 2);
+    const float *ap = attn + qm * (long)(d.L * P);
+    float *glp = grad_loc + qm * (long)(d.L * P * 2);
+    float *gap = grad_attn + qm * (long)(d.L * P);
+    const int xs = d.M * D;
+
+    float g[VEC];
+    Vec<VT>::load(grad_out + qm * D + gl * VEC, g);
+
+    for (int l = 0; l < d.L; ++l) {
+        const LevelInfo li = s_lv[l];
+        const long lvl_off = (long)li.start * xs;
+        const VT *vl = vimg + lvl_off;
+        float *gvl = gvimg + lvl_off;
+        const int ys = li.W * xs;
+
+        float lxy[2 * P], aw[P];
+#pragma unroll
+        for (int i = 0; i < P / 2; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(lp) + i);
+            lxy[4 * i] = t.x; lxy[4 * i + 1] = t.y; lxy[4 * i + 2] = t.z; lxy[4 * i + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < P / 4; ++i) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(ap) + i);
+            aw[4 * i] = t.x; aw[4 * i + 1] = t.y; aw[4 * i + 2] = t.z; aw[4 * i + 3] = t.w;
+        }
+        lp += 2 * P;
+        ap += P;
+
+        float pxy[2 * P], pa[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            pxy[2 * p] = 0.f; pxy[2 * p + 1] = 0.f; pa[p] = 0.f;
+            const Tap<float> t = make_tap(lxy[2 * p], lxy[2 * p + 1], li.H, li.W);
+            if (!t.inside || !w.valid) continue;
+            const bool y0ok = t.y0 >= 0, y1ok = t.y0 + 1 <= li.H - 1;
+            const bool x0ok = t.x0 >= 0, x1ok = t.x0 + 1 <= li.W - 1;
+            const int o00 = t.y0 * ys + t.x0 * xs;
+            float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) v00[c] = v01[c] = v10[c] = v11[c] = 0.f;
+            if (y0ok && x0ok) Vec<VT>::load(vl + o00, v00);
+            if (y0ok && x1ok) Vec<VT>::load(vl + o00 + xs, v01);
+            if (y1ok && x0ok) Vec<VT>::load(vl + o00 + ys, v10);
+            if (y1ok && x1ok) Vec<VT>::load(vl + o00 + ys + xs, v11);
+            const float hy = 1.f - t.ly, hx = 1.f - t.lx;
+            const float w00 = hy * hx, w01 = hy * t.lx, w10 = t.ly * hx, w11 = t.ly * t.lx;
+            const float a = aw[p];
+            float sx = 0.f, sy = 0.f, sa = 0.f;
+            float tg[VEC];
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                tg[c] = g[c] * a;                                          // cuh:111
+                const float dgx = hy * (v01[c] - v00[c]) + t.ly * (v11[c] - v10[c]);   // cuh:119-149
+                const float dgy = hx * (v10[c] - v00[c]) + t.lx * (v11[c] - v01[c]);
+                sx += dgx * tg[c];
+                sy += dgy * tg[c];
+                sa += g[c] * (w00 * v00[c] + w01 * v01[c] + w10 * v10[c] + w11 * v11[c]);  // cuh:155-156
+            }
+            pxy[2 * p] = (float)li.W * sx;                                 // cuh:157
+            pxy[2 * p + 1] = (float)li.H * sy;                             // cuh:158
+            pa[p] = sa;
+#pragma unroll
+            for (int c = 0; c < VEC; c += 4) {
+                if (y0ok && x0ok)
+                    red_add_f32x4(gvl + o00 + c, w00 * tg[c], w00 * tg[c + 1], w00 * tg[c + 2], w00 * tg[c + 3]);
+                if (y0ok && x1ok)
+                    red_add_f32x4(gvl + o00 + xs + c, w01 * tg[c], w01 * tg[c + 1], w01 * tg[c + 2], w01 * tg[c + 3]);
+                if (y1ok && x0ok)
+                    red_add_f32x4(gvl + o00 + ys + c, w10 * tg[c], w10 * tg[c + 1], w10 * tg[c + 2], w10 * tg[c + 3]);
+                if (y1ok && x1ok)
+                    red_add_f32x4(gvl + o00 + ys + xs + c, w11 * tg[c], w11 * tg[c + 1], w11 * tg[c + 2], w11 * tg[c + 3]);
+            }
+        }
+        group_reduce_scatter<G, 2 * P>(pxy, gl);
+        group_reduce_scatter<G, P>(pa, gl);
+        if (w.valid) {
+            group_store<G, 2 * P>(glp, pxy, gl);
+            group_store<G, P>(gap, pa, gl);
+        }
+        glp += 2 * P;
+        gap += P;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel: one warp per (n, q, m); lanes stride over channels; any D / P / alignment.
+// VT value & grad_out type, CT arithmetic / loc / attn / all-gradients type.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ld_ct(const float *p, float) { return *p; }
+__device__ __forceinline__ double ld_ct(const double *p, double) { return *p; }
+__device__ __forceinline__ float ld_ct(const __nv_bfloat16 *p, float) { return __bfloat162float(*p); }
+
+template <typename VT, typename CT>
+__global__ void __launch_bounds__(256)
+bwd_generic_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
+                   const int64_t *__restrict__ lsi, const CT *__restrict__ loc,
+                   const CT *__restrict__ attn, const VT *__restrict__ grad_out,
+                   CT *__restrict__ grad_value, CT *__restrict__ grad_loc,
+                   CT *__restrict__ grad_attn, const Dims d)
+{
+    __shared__ LevelInfo s_lv[MSDA_MAX_LEVELS];
+    stage_levels(s_lv, shapes, lsi, d.L);
+
+    const int lane = threadIdx.x & 31;
+    const long qm = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qm >= (long)d.N * d.Lq * d.M) return;          // whole warp leaves together
+    const int m = (int)(qm % d.M);
+    const long n = qm / ((long)d.Lq * d.M);
+
+    const long xs = (long)d.M * d.D;
+    const long img = (n * d.S * d.M + m) * (long)d.D;
+    const VT *gq = grad_out + qm * d.D;
+    const CT *lp = loc + qm * (long)d.L * d.P * 2;
+    const CT *ap = attn + qm * (long)d.L * d.P;
+    CT *glp = grad_loc + qm * (long)d.L * d.P * 2;
+    CT *gap = grad_attn + qm * (long)d.L * d.P;
+
+    for (int l = 0; l < d.L; ++l) {
+        const LevelInfo li = s_lv[l];
+        const long base = img + (long)li.start * xs;
+        const long ys = (long)li.W * xs;
+        for (int p = 0; p < d.P; ++p, lp += 2, ++ap, glp += 2, ++gap) {
+            const Tap<CT> t = make_tap(lp[0], lp[1], li.H, li.W);
+            CT sx = 0, sy = 0, sa = 0;
+            if (t.inside) {
+                const bool y0ok = t.y0 >= 0, y1ok = t.y0 + 1 <= li.H - 1;
+                const bool x0ok = t.x0 >= 0, x1ok = t.x0 + 1 <= li.W - 1;
+                const long o00 = base + t.y0 * ys + t.x0 * xs;
+                const CT hy = CT(1) - t.ly, hx = CT(1) - t.lx;
+                const CT w00 = hy * hx, w01 = hy * t.lx, w10 = t.ly * hx, w11 = t.ly * t.lx;
+                const CT a = ap[0];
+                for (int c = lane; c < d.D; c += 32) {
+                    const CT gc = ld_ct(gq + c, CT());
+                    const CT tg = gc * a;
+                    CT v00 = 0, v01 = 0, v10 = 0, v11 = 0;
+                    if (y0ok && x0ok) { v00 = ld_ct(value + o00 + c, CT()); atomicAdd(grad_value + o00 + c, w00 * tg); }
+                    if (y0ok && x1ok) { v01 = ld_ct(value + o00 + xs + c, CT()); atomicAdd(grad_value + o00 + xs + c, w01 * tg); }
+                    if (y1ok && x0ok) { v10 = ld_ct(value + o00 + ys + c, CT()); atomicAdd(grad_value + o00 + ys + c, w10 * tg); }
+                    if (y1ok && x1ok) { v11 = ld_ct(value + o00 + ys + xs + c, CT()); atomicAdd(grad_value + o00 + ys + xs + c, w11 * tg); }
+                    sx += (hy * (v01 - v00) + t.ly * (v11 - v10)) * tg;
+                    sy += (hx * (v10 - v00) + t.lx * (v11 - v01)) * tg;
+                    sa += gc * (w00 * v00 + w01 * v01 + w10 * v10 + w11 * v11);
+                }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                sx += __shfl_xor_sync(kFullMask, sx, off);
+                sy += __shfl_xor_sync(kFullMask, sy, off);
+                sa += __shfl_xor_sync(kFullMask, sa, off);
+            }
+            if (lane == 0) {
+                glp[0] = (CT)li.W * sx;
+                glp[1] = (CT)li.H * sy;
+                gap[0] = sa;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <typename VT>
+constexpr bool vec_supported(int D, int P)
+{
+    if (P != 4) return false;
+    if (sizeof(VT) == 4) return D == 16 || D == 32 || D == 64;
+    return D == 32 || D == 64;
+}
+
+template <typename VT>
+bool use_vec(const Dims &d, bool vec_ok)
+{
+    return vec_ok && tuning().bwd_variant != 99 && vec_supported<VT>(d.D, d.P) &&
+           (long)d.S * d.M * d.D < (1L << 31);
+}
+
+template <typename VT, int D, int P>
+int run_vec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+            const void *attn, const void *grad_out, void *gv, void *gl, void *ga, const Dims &d,
+            cudaStream_t st)
+{
+    constexpr int QPW = 32 / (D / Vec<VT>::N);
+    const int threads = tuning().block_threads > 0 ? tuning().block_threads : 256;
+    const int order = tuning().bwd_variant >= 0 ? tuning().bwd_variant : 1;
+    const long grid = grid_for(d, order, QPW, threads);
+    bwd_vec_kernel<VT, D, P><<<(unsigned)grid, threads, 0, st>>>(
+        (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,
+        (float *)gv, (float *)gl, (float *)ga, d, order);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+template <typename VT, typename CT>
+int run_generic(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                const void *attn, const void *grad_out, void *gv, void *gl, void *ga, const Dims &d,
+                cudaStream_t st)
+{
+    const long warps = (long)d.N * d.Lq * d.M;
+    const int threads = 256;
+    const long grid = (warps + (threads / 32) - 1) / (threads / 32);
+    bwd_generic_kernel<VT, CT><<<(unsigned)grid, threads, 0, st>>>(
+        (const VT *)value, shapes, lsi, (const CT *)loc, (const CT *)attn, (const VT *)grad_out,
+        (CT *)gv, (CT *)gl, (CT *)ga, d);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+const char *backward_kernel_name(DType dt, int D, int L, int P, bool vec_ok)
+{
+    (void)L;
+    Dims d{1, 1, 1, D, 1, 1, P};
+    switch (dt) {
+    case DType::F64: return "bwd_generic_f64";
+    case DType::F32: return use_vec<float>(d, vec_ok) ? "bwd_vec_f32" : "bwd_generic_f32";
+    case DType::BF16: return use_vec<__nv_bfloat16>(d, vec_ok) ? "bwd_vec_bf16" : "bwd_generic_bf16";
+    }
+    return "?";
+}
+
+int launch_backward(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi,
+                    const void *loc, const void *attn, const void *grad_out, void *gv, void *gl,
+                    void *ga, const Dims &d, bool vec_ok, cudaStream_t st)
+{
+    const size_t gv_elt = (dt == DType::F64) ? 8 : 4;
+    const size_t gv_bytes = gv_elt * (size_t)d.N * d.S * d.M * d.D;
+    if (gv_bytes) {
+        cudaError_t e = cudaMemsetAsync(gv, 0, gv_bytes, st);      // ms_deform_attn_cuda.cu:121
+        if (e != cudaSuccess) return (int)e;
+    }
+    if ((long)d.N * d.Lq * d.M == 0) return 0;
+#define ARGS value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st
+    if (dt == DType::F64) return run_generic<double, double>(ARGS);
+    if (dt == DType::F32) {
+        if (use_vec<float>(d, vec_ok)) {
+            switch (d.D) {
+            case 16: return run_vec<float, 16, 4>(ARGS);
+            case 32: return run_vec<float, 32, 4>(ARGS);
+            case 64: return run_vec<float, 64, 4>(ARGS);
+            }
+        }
+        return run_generic<float, float>(ARGS);
+    }
+    if (use_vec<__nv_bfloat16>(d, vec_ok)) {
+        switch (d.D) {
+        case 32: return run_vec<__nv_bfloat16, 32, 4>(ARGS);
+        case 64: return run_vec<__nv_bfloat16, 64, 4>(ARGS);
+        }
+    }
+    return run_generic<__nv_bfloat16, float>(ARGS);
+#undef ARGS
+}
+
+}  // namespace msda

@@ -1,0 +1,183 @@
+// msda_capi.cu -- the extern "C" surface declared in include/msda_b200.h.
+// Argument validation mirrors what the reference's host wrapper asserts
+// (MonoDETR/lib/models/monodetr/ops/src/cuda/ms_deform_attn_cuda.cu:28-52, 93-119) as far as a
+// raw-pointer interface can (contiguity / device placement are the Python layer's job).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "msda_common.cuh"
+
+#define MSDA_STR2(x) #x
+#define MSDA_STR(x) MSDA_STR2(x)
+
+namespace msda {
+
+static Tuning g_tuning;
+Tuning &tuning() { return g_tuning; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static thread_local char t_err[256] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int cuda_result(int e, const char *what)
+{
+    if (e == 0) {
+        t_err[0] = 0;
+        return 0;
+    }
+    snprintf(t_err, sizeof(t_err), "%s: %s (cudaError %d)", what, cudaGetErrorString((cudaError_t)e), e);
+    return e;
+}
+
+static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+struct Checked {
+    Dims d;
+    bool vec_ok;
+    bool empty_out;
+};
+
+static int check_common(const char *fn, DType dt, const void *value, const int64_t *shapes,
+                        const int64_t *lsi, const void *loc, const void *attn, int N, int S, int M,
+                        int D, int L, int Lq, int P, Checked *out)
+{
+    if (N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0)
+        return fail(MSDA_ERR_BAD_SHAPE, "%s: negative dimension (N=%d S=%d M=%d D=%d L=%d Lq=%d P=%d)", fn, N, S, M,
+                    D, L, Lq, P);
+    if (L > MSDA_MAX_LEVELS)
+        return fail(MSDA_ERR_BAD_SHAPE, "%s: L=%d exceeds MSDA_MAX_LEVELS=%d", fn, L, MSDA_MAX_LEVELS);
+    const long long big = 1LL << 62;
+    const long long nv = (long long)N * S * M * D, nl = (long long)N * Lq * M * L * P * 2;
+    if (nv < 0 || nv > big || nl < 0 || nl > big)
+        return fail(MSDA_ERR_BAD_SHAPE, "%s: tensor size overflows", fn);
+    const bool has_samples = (long long)N * Lq * M * L * P > 0;
+    if (L > 0 && (!shapes || !lsi))
+        return fail(MSDA_ERR_NULL_POINTER, "%s: spatial_shapes / level_start_index is NULL", fn);
+    if (nv > 0 && !value) return fail(MSDA_ERR_NULL_POINTER, "%s: value is NULL", fn);
+    if (has_samples && (!loc || !attn)) return fail(MSDA_ERR_NULL_POINTER, "%s: sampling_loc / attn_weight is NULL", fn);
+    const size_t ve = dt == DType::F64 ? 8 : (dt == DType::F32 ? 4 : 2);
+    const size_t ce = dt == DType::F64 ? 8 : 4;
+    if (!aligned(value, ve) || !aligned(loc, ce) || !aligned(attn, ce) || !aligned(shapes, 8) || !aligned(lsi, 8))
+        return fail(MSDA_ERR_MISALIGNED, "%s: a pointer is not aligned to its element size", fn);
+    out->d = Dims{N, S, M, D, L, Lq, P};
+    out->vec_ok = aligned(value, 16) && aligned(loc, 16) && aligned(attn, 16);
+    out->empty_out = (long long)N * Lq * M * D == 0;
+    return 0;
+}
+
+static int forward_impl(const char *fn, DType dt, const void *value, const int64_t *shapes,
+                        const int64_t *lsi, const void *loc, const void *attn, void *out, int N, int S,
+                        int M, int D, int L, int Lq, int P, void *stream)
+{
+    Checked c;
+    if (int rc = check_common(fn, dt, value, shapes, lsi, loc, attn, N, S, M, D, L, Lq, P, &c)) return rc;
+    if (c.empty_out) return cuda_result(0, fn);
+    if (!out) return fail(MSDA_ERR_NULL_POINTER, "%s: out is NULL", fn);
+    c.vec_ok = c.vec_ok && aligned(out, 16);
+    return cuda_result(launch_forward(dt, value, shapes, lsi, loc, attn, out, c.d, c.vec_ok, (cudaStream_t)stream), fn);
+}
+
+static int backward_impl(const char *fn, DType dt, const void *value, const int64_t *shapes,
+                         const int64_t *lsi, const void *loc, const void *attn, const void *grad_out,
+                         void *gv, void *gl, void *ga, int N, int S, int M, int D, int L, int Lq, int P,
+                         void *stream)
+{
+    Checked c;
+    if (int rc = check_common(fn, dt, value, shapes, lsi, loc, attn, N, S, M, D, L, Lq, P, &c)) return rc;
+    const bool has_value = (long long)N * S * M * D > 0;
+    const bool has_samples = (long long)N * Lq * M * L * P > 0;
+    if (has_value && !gv) return fail(MSDA_ERR_NULL_POINTER, "%s: grad_value is NULL", fn);
+    if (has_samples && (!gl || !ga)) return fail(MSDA_ERR_NULL_POINTER, "%s: grad_loc / grad_attn is NULL", fn);
+    if (!c.empty_out && !grad_out) return fail(MSDA_ERR_NULL_POINTER, "%s: grad_out is NULL", fn);
+    c.vec_ok = c.vec_ok && aligned(grad_out, 16) && aligned(gv, 16) && aligned(gl, 16) && aligned(ga, 16);
+    return cuda_result(
+        launch_backward(dt, value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, c.d, c.vec_ok, (cudaStream_t)stream), fn);
+}
+
+}  // namespace msda
+
+using namespace msda;
+
+#define FWD_ARGS                                                                                     \
+    const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,              \
+        const void *sampling_loc, const void *attn_weight, void *out, int N, int S, int M, int D,    \
+        int L, int Lq, int P, void *stream
+#define FWD_PASS value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out, N, S, M, D, L, Lq, P, stream
+#define BWD_ARGS                                                                                     \
+    const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,              \
+        const void *sampling_loc, const void *attn_weight, const void *grad_out, void *grad_value,   \
+        void *grad_loc, void *grad_attn, int N, int S, int M, int D, int L, int Lq, int P, void *stream
+#define BWD_PASS                                                                                     \
+    value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_out, grad_value,       \
+        grad_loc, grad_attn, N, S, M, D, L, Lq, P, stream
+
+extern "C" {
+
+int msda_forward_f32(FWD_ARGS) { return forward_impl("msda_forward_f32", DType::F32, FWD_PASS); }
+int msda_forward_f64(FWD_ARGS) { return forward_impl("msda_forward_f64", DType::F64, FWD_PASS); }
+int msda_forward_bf16(FWD_ARGS) { return forward_impl("msda_forward_bf16", DType::BF16, FWD_PASS); }
+int msda_backward_f32(BWD_ARGS) { return backward_impl("msda_backward_f32", DType::F32, BWD_PASS); }
+int msda_backward_f64(BWD_ARGS) { return backward_impl("msda_backward_f64", DType::F64, BWD_PASS); }
+int msda_backward_bf16(BWD_ARGS) { return backward_impl("msda_backward_bf16", DType::BF16, BWD_PASS); }
+
+int msda_abi_version(void) { return MSDA_ABI_VERSION; }
+
+const char *msda_build_info(void)
+{
+    return "libmsda_b200 sm_100a nvcc " MSDA_STR(__CUDACC_VER_MAJOR__) "." MSDA_STR(__CUDACC_VER_MINOR__) " built " __DATE__;
+}
+
+const char *msda_last_error(void) { return t_err; }
+
+long long msda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+static int *tuning_slot(const char *key)
+{
+    if (!key) return nullptr;
+    if (!strcmp(key, "fwd_variant")) return &tuning().fwd_variant;
+    if (!strcmp(key, "bwd_variant")) return &tuning().bwd_variant;
+    if (!strcmp(key, "block_threads")) return &tuning().block_threads;
+    return nullptr;
+}
+
+int msda_set_tuning(const char *key, int value)
+{
+    int *slot = tuning_slot(key);
+    if (!slot) return fail(MSDA_ERR_BAD_SHAPE, "msda_set_tuning: unknown key '%s'", key ? key : "(null)");
+    if (!strcmp(key, "block_threads") && value > 0 && (value % 32 != 0 || value > 512))
+        return fail(MSDA_ERR_BAD_SHAPE, "msda_set_tuning: block_threads must be a multiple of 32, <= 512");
+    *slot = value;
+    return 0;
+}
+
+int msda_get_tuning(const char *key)
+{
+    int *slot = tuning_slot(key);
+    return slot ? *slot : -1;
+}
+
+static DType dtype_of(int bits, int is_bf16) { return is_bf16 ? DType::BF16 : (bits == 64 ? DType::F64 : DType::F32); }
+
+const char *msda_describe_forward(int dtype_bits, int is_bf16, int D, int L, int P)
+{
+    return forward_kernel_name(dtype_of(dtype_bits, is_bf16), D, L, P, true);
+}
+
+const char *msda_describe_backward(int dtype_bits, int is_bf16, int D, int L, int P)
+{
+    return backward_kernel_name(dtype_of(dtype_bits, is_bf16), D, L, P, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,253 @@
+// msda_common.cuh -- shared device helpers for the sm_100a MSDA kernels.
+//
+// Semantics reproduced (reference = MonoDETR/lib/models/monodetr/ops/src/cuda/
+// ms_deform_im2col_cuda.cuh): sample coordinate and in-range window :285-291, bilinear
+// taps with per-corner zero padding :33-84, gradient formulas :87-159.  The code below is
+// organised around 128-bit channel vectors and lane groups, not around the reference's
+// one-thread-per-channel layout.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "msda_b200.h"
+
+namespace msda {
+
+struct Dims {
+    int N, S, M, D, L, Lq, P;
+};
+
+struct LevelInfo {
+    int H, W, start, pad;
+};
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// spatial_shapes / level_start_index live in device memory (int64, as the reference passes
+// them); every CTA stages them once so that no thread re-reads them per sample and the host
+// never has to look at them (CUDA-graph safe).
+__device__ __forceinline__ void stage_levels(LevelInfo *s_lv, const int64_t *__restrict__ shapes,
+                                             const int64_t *__restrict__ lsi, int L)
+{
+    if (threadIdx.x < (unsigned)L) {
+        LevelInfo li;
+        li.H = (int)shapes[2 * threadIdx.x];
+        li.W = (int)shapes[2 * threadIdx.x + 1];
+        li.start = (int)lsi[threadIdx.x];
+        li.pad = 0;
+        s_lv[threadIdx.x] = li;
+    }
+    __syncthreads();
+}
+
+// One bilinear sample: integer corner, fractional parts, per-corner validity.
+template <typename CT>
+struct Tap {
+    int y0, x0;
+    CT ly, lx;
+    bool inside;
+};
+
+// cuh:285-288.  The product is rounded before the subtraction (no FMA contraction) so that
+// floor() lands exactly where the reference's scalar_t arithmetic puts it.
+__device__ __forceinline__ Tap<float> make_tap(float loc_x, float loc_y, int H, int W)
+{
+    Tap<float> t;
+    const float py = __fmul_rn(loc_y, (float)H) - 0.5f;
+    const float px = __fmul_rn(loc_x, (float)W) - 0.5f;
+    t.inside = (py > -1.f) && (px > -1.f) && (py < (float)H) && (px < (float)W);
+    const float fy = floorf(py), fx = floorf(px);
+    t.y0 = (int)fy;
+    t.x0 = (int)fx;
+    t.ly = py - fy;
+    t.lx = px - fx;
+    return t;
+}
+
+__device__ __forceinline__ Tap<double> make_tap(double loc_x, double loc_y, int H, int W)
+{
+    Tap<double> t;
+    const double py = __dmul_rn(loc_y, (double)H) - 0.5;
+    const double px = __dmul_rn(loc_x, (double)W) - 0.5;
+    t.inside = (py > -1.0) && (px > -1.0) && (py < (double)H) && (px < (double)W);
+    const double fy = floor(py), fx = floor(px);
+    t.y0 = (int)fy;
+    t.x0 = (int)fx;
+    t.ly = py - fy;
+    t.lx = px - fx;
+    return t;
+}
+
+// ---- 128-bit channel vectors ---------------------------------------------------------------
+template <typename VT>
+struct Vec;
+
+template <>
+struct Vec<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const float *p, float (&f)[4])
+    {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&f)[4])
+    {
+        *reinterpret_cast<float4 *>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+};
+
+template <>
+struct Vec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&f)[8])
+    {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {          // bf16 -> fp32 is a 16-bit shift
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&f)[8])
+    {
+        unsigned w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<const unsigned *>(&h);
+        }
+        *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+// REDG.E.ADD.F32x4: one 16-byte reduction per lane instead of four scalar atomics.
+__device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+// ---- lane-group reduce-scatter ---------------------------------------------------------------
+// G lanes (a power of two, aligned inside the warp) each hold NV partial sums (NV a power of
+// two).  Butterfly: at every step a lane keeps one half of its values and ships the other half
+// to its partner, so log2(G) steps cost NV/2 + NV/4 + ... shuffles instead of NV*log2(G).
+// Afterwards (gl = lane index inside the group):
+//   NV >= G : v[0 .. NV/G) are the totals of elements [gl*NV/G, (gl+1)*NV/G)
+//   NV <  G : v[0] is the total of element gl / (G/NV)   (duplicated across G/NV lanes)
+template <int OFF, int NV>
+struct ReduceScatter {
+    static __device__ __forceinline__ void run(float *v, int gl)
+    {
+        if constexpr (OFF >= 1) {
+            if constexpr (NV >= 2) {
+                constexpr int H = NV / 2;
+                const bool upper = (gl & OFF) != 0;
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    const float send = upper ? v[i] : v[i + H];
+                    const float keep = upper ? v[i + H] : v[i];
+                    v[i] = keep + __shfl_xor_sync(kFullMask, send, OFF);
+                }
+                ReduceScatter<OFF / 2, H>::run(v, gl);
+            } else {
+                v[0] += __shfl_xor_sync(kFullMask, v[0], OFF);
+                ReduceScatter<OFF / 2, 1>::run(v, gl);
+            }
+        }
+    }
+};
+
+template <int G, int NV>
+__device__ __forceinline__ void group_reduce_scatter(float (&v)[NV], int gl)
+{
+    static_assert((G & (G - 1)) == 0 && (NV & (NV - 1)) == 0, "power-of-two sizes only");
+    ReduceScatter<G / 2, NV>::run(v, gl);
+}
+
+// store the result of group_reduce_scatter as a contiguous run of NV floats at dst
+template <int G, int NV>
+__device__ __forceinline__ void group_store(float *dst, const float (&v)[NV], int gl)
+{
+    if constexpr (NV >= G) {
+        constexpr int CNT = NV / G;
+#pragma unroll
+        for (int i = 0; i < CNT; ++i) dst[gl * CNT + i] = v[i];
+    } else {
+        constexpr int REP = G / NV;
+        if ((gl % REP) == 0) dst[gl / REP] = v[0];
+    }
+}
+
+// ---- work decomposition ----------------------------------------------------------------------
+// A warp owns QPW = 32/G consecutive queries of ONE head (lane group k -> query chunk*QPW+k),
+// so that neighbouring queries -- which sample neighbouring pixels -- share L1 lines and, on
+// coarse levels, coalesce into the same 128-byte line within one load instruction.
+//   order 0 : consecutive warps walk the heads of one query chunk, then the next chunk
+//   order 1 : a CTA's warps walk consecutive query chunks of one head (larger per-head tiles)
+struct WorkItem {
+    int n, q, m;
+    bool valid;
+};
+
+template <int QPW>
+__device__ __forceinline__ WorkItem decode_work(const Dims &d, int order, int k)
+{
+    const int warps_per_block = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    const int n_chunks = (d.Lq + QPW - 1) / QPW;
+    WorkItem w;
+    long chunk;
+    if (order == 0) {
+        const long wg = (long)blockIdx.x * warps_per_block + warp;
+        w.m = (int)(wg % d.M);
+        const long r = wg / d.M;
+        chunk = r % n_chunks;
+        w.n = (int)(r / n_chunks);
+    } else {
+        const int n_tiles = (n_chunks + warps_per_block - 1) / warps_per_block;
+        const long b = blockIdx.x;
+        w.m = (int)(b % d.M);
+        const long r = b / d.M;
+        chunk = (r % n_tiles) * warps_per_block + warp;
+        w.n = (int)(r / n_tiles);
+    }
+    w.q = (int)(chunk * QPW + k);
+    w.valid = (w.n < d.N) && (chunk < n_chunks) && (w.q < d.Lq);
+    return w;
+}
+
+inline long grid_for(const Dims &d, int order, int qpw, int threads)
+{
+    const long wpb = threads / 32;
+    const long n_chunks = (d.Lq + qpw - 1) / qpw;
+    if (order == 0) return ((long)d.N * n_chunks * d.M + wpb - 1) / wpb;
+    const long n_tiles = (n_chunks + wpb - 1) / wpb;
+    return (long)d.N * n_tiles * d.M;
+}
+
+// ---- host-side launch plumbing (msda_capi.cu) ------------------------------------------------
+struct Tuning {
+    int fwd_variant = -1;
+    int bwd_variant = -1;
+    int block_threads = -1;
+};
+Tuning &tuning();
+void count_launch(int n = 1);
+
+// dtype tags for the launchers
+enum class DType { F32, F64, BF16 };
+
+// implemented in msda_forward.cu / msda_backward.cu; return cudaError_t
+int launch_forward(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi,
+                   const void *loc, const void *attn, void *out, const Dims &d, bool vec_ok,
+                   cudaStream_t st);
+int launch_backward(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi,
+                    const void *loc, const void *attn, const void *grad_out, void *grad_value,
+                    void *grad_loc, void *grad_attn, const Dims &d, bool vec_ok, cudaStream_t st);
+const char *forward_kernel_name(DType dt, int D, int L, int P, bool vec_ok);
+const char *backward_kernel_name(DType dt, int D, int L, int P, bool vec_ok);
+
+}  // namespace msda

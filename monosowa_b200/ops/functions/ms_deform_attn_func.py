@@ -1,0 +1,192 @@
+"""Autograd boundary of the MSDA op -- drop-in for the reference's
+MonoDETR/lib/models/monodetr/ops/functions/ms_deform_attn_func.py:21-38.
+
+``MSDeformAttnFunction.apply(value, value_spatial_shapes, value_level_start_index,
+sampling_locations, attention_weights, im2col_step)`` keeps the reference signature, return
+shape ``(N, Lq, M*D)`` and gradient tuple ``(grad_value, None, None, grad_sampling_loc,
+grad_attn_weight, None)``.  Underneath, instead of the pybind11 extension
+``MultiScaleDeformableAttention`` (src/vision.cpp:13-16), two ``torch.library`` ops
+``msda::forward`` / ``msda::backward`` call the C ABI of libmsda_b200.so through ctypes.
+
+Error behaviour mirrors the reference host wrapper (src/cuda/ms_deform_attn_cuda.cu:28-52):
+RuntimeError for non-contiguous inputs and for ``batch % min(batch, im2col_step) != 0``;
+CPU tensors raise NotImplementedError (the reference: AT_ERROR("Not implemented on the CPU"),
+src/ms_deform_attn.h:38) -- there is no CPU fallback by design.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ... import _lib
+
+_SUFFIX = {torch.float32: "f32", torch.float64: "f64", torch.bfloat16: "bf16"}
+_LIBDEF = torch.library.Library("msda", "DEF")
+_LIBDEF.define("forward(Tensor value, Tensor spatial_shapes, Tensor level_start_index, "
+               "Tensor sampling_locations, Tensor attention_weights, int im2col_step) -> Tensor")
+_LIBDEF.define("backward(Tensor value, Tensor spatial_shapes, Tensor level_start_index, "
+               "Tensor sampling_locations, Tensor attention_weights, Tensor grad_output, "
+               "int im2col_step) -> (Tensor, Tensor, Tensor)")
+
+
+def _check(value, spatial_shapes, level_start_index, loc, attn, im2col_step, grad_output=None):
+    named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("sampling_loc", loc), ("attn_weight", attn)]
+    if grad_output is not None:
+        named.append(("grad_output", grad_output))
+    for name, t in named:
+        if not t.is_cuda:
+            raise NotImplementedError(f"{name} must be a CUDA tensor: MSDA is not implemented on the CPU "
+                                      "(no fallback; see oracle/ for the test-only CPU restatement)")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+        if t.device != value.device:
+            raise RuntimeError(f"{name} is on {t.device}, value is on {value.device}")
+    if value.dtype not in _SUFFIX:
+        raise RuntimeError(f"unsupported value dtype {value.dtype} (float32, float64, bfloat16)")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes and level_start_index must be int64 tensors")
+    if value.dim() != 4 or loc.dim() != 6 or attn.dim() != 5 or spatial_shapes.dim() != 2:
+        raise RuntimeError("expected value (N,S,M,D), sampling_loc (N,Lq,M,L,P,2), attn_weight (N,Lq,M,L,P), "
+                           "spatial_shapes (L,2)")
+    n, s, m, d = value.shape
+    _, lq, m2, nl, p, two = loc.shape
+    if (loc.shape[0] != n or m2 != m or two != 2 or tuple(attn.shape) != (n, lq, m, nl, p)
+            or spatial_shapes.shape[0] != nl or spatial_shapes.shape[1] != 2 or level_start_index.numel() != nl):
+        raise RuntimeError(f"inconsistent shapes: value {tuple(value.shape)}, sampling_loc {tuple(loc.shape)}, "
+                           f"attn_weight {tuple(attn.shape)}, spatial_shapes {tuple(spatial_shapes.shape)}")
+    step = min(n, int(im2col_step))
+    if n > 0 and (step <= 0 or n % step != 0):                                  # ms_deform_attn_cuda.cu:50-52
+        raise RuntimeError(f"batch({n}) must divide im2col_step({step})")
+    return n, s, m, d, nl, lq, p
+
+
+def _coord_dtype(value):
+    return torch.float64 if value.dtype == torch.float64 else torch.float32
+
+
+def _as_coord(t, value):
+    want = _coord_dtype(value)
+    return t if t.dtype == want else t.to(want)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _raise(rc, what):
+    raise RuntimeError(f"{what} failed (code {rc}): {_lib.last_error()}")
+
+
+def _forward_cuda(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step):
+    n, s, m, d, nl, lq, p = _check(value, spatial_shapes, level_start_index, sampling_locations,
+                                   attention_weights, im2col_step)
+    loc, attn = _as_coord(sampling_locations, value), _as_coord(attention_weights, value)
+    out = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
+    fn = getattr(_lib.lib, "msda_forward_" + _SUFFIX[value.dtype])
+    with torch.cuda.device(value.device):
+        rc = fn(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(loc), _ptr(attn), _ptr(out),
+                n, s, m, d, nl, lq, p, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        _raise(rc, "msda::forward")
+    return out
+
+
+def _backward_cuda(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                   grad_output, im2col_step):
+    grad_output = grad_output.contiguous()
+    n, s, m, d, nl, lq, p = _check(value, spatial_shapes, level_start_index, sampling_locations,
+                                   attention_weights, im2col_step, grad_output)
+    if grad_output.numel() != n * lq * m * d:
+        raise RuntimeError(f"grad_output has {grad_output.numel()} elements, expected {n * lq * m * d}")
+    if grad_output.dtype != value.dtype:
+        grad_output = grad_output.to(value.dtype)
+    loc, attn = _as_coord(sampling_locations, value), _as_coord(attention_weights, value)
+    ct = _coord_dtype(value)
+    grad_value = torch.empty(value.shape, dtype=ct, device=value.device)        # zero-filled by the library
+    grad_loc = torch.empty(loc.shape, dtype=ct, device=value.device)
+    grad_attn = torch.empty(attn.shape, dtype=ct, device=value.device)
+    fn = getattr(_lib.lib, "msda_backward_" + _SUFFIX[value.dtype])
+    with torch.cuda.device(value.device):
+        rc = fn(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(loc), _ptr(attn),
+                _ptr(grad_output), _ptr(grad_value), _ptr(grad_loc), _ptr(grad_attn),
+                n, s, m, d, nl, lq, p, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        _raise(rc, "msda::backward")
+    if grad_value.dtype != value.dtype:                       # bf16: fp32 accumulation, narrowed once
+        grad_value = grad_value.to(value.dtype)
+    if grad_loc.dtype != sampling_locations.dtype:
+        grad_loc = grad_loc.to(sampling_locations.dtype)
+    if grad_attn.dtype != attention_weights.dtype:
+        grad_attn = grad_attn.to(attention_weights.dtype)
+    return grad_value, grad_loc, grad_attn
+
+
+_LIBIMPL = torch.library.Library("msda", "IMPL")
+_LIBIMPL.impl("forward", _forward_cuda, "CUDA")
+_LIBIMPL.impl("backward", _backward_cuda, "CUDA")
+
+
+@torch.library.register_fake("msda::forward")
+def _forward_fake(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step):
+    n, _, m, d = value.shape
+    return value.new_empty((n, sampling_locations.shape[1], m * d))
+
+
+@torch.library.register_fake("msda::backward")
+def _backward_fake(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                   grad_output, im2col_step):
+    return (torch.empty_like(value), torch.empty_like(sampling_locations), torch.empty_like(attention_weights))
+
+
+def _setup_context(ctx, inputs, output):
+    value, shapes, lsi, loc, attn, step = inputs
+    ctx.im2col_step = step
+    ctx.save_for_backward(value, shapes, lsi, loc, attn)
+
+
+def _autograd_backward(ctx, grad_output):
+    value, shapes, lsi, loc, attn = ctx.saved_tensors
+    gv, gl, ga = torch.ops.msda.backward(value, shapes, lsi, loc, attn, grad_output, ctx.im2col_step)
+    return gv, None, None, gl, ga, None
+
+
+torch.library.register_autograd("msda::forward", _autograd_backward, setup_context=_setup_context)
+
+
+class MSDeformAttnFunction(Function):
+    """Same contract as the reference class (ms_deform_attn_func.py:21-38)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        output = torch.ops.msda.forward(value, value_spatial_shapes, value_level_start_index,
+                                        sampling_locations, attention_weights, ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights = ctx.saved_tensors
+        grad_value, grad_sampling_loc, grad_attn_weight = torch.ops.msda.backward(
+            value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+            grad_output, ctx.im2col_step)
+        return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    """Name-compatible with the pybind export ``MSDA.ms_deform_attn_forward`` (src/vision.cpp:14)."""
+    return torch.ops.msda.forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step)
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step):
+    """Name-compatible with ``MSDA.ms_deform_attn_backward`` (src/vision.cpp:15); returns a list of 3."""
+    return list(torch.ops.msda.backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                        grad_output, im2col_step))

@@ -1,0 +1,474 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI, via MSDeformAttnFunction / torch.ops.msda)
+against the oracle on identical seeded inputs.  Run on the B200 box:  pytest tests -m gpu
+
+Tolerance contract (BASELINE.json north_star) -- kernel vs the fp64 oracle evaluated
+on the SAME (already rounded) inputs:
+  fp64 : rel-L2 <= 1e-12 everywhere (arithmetic order differs from grid_sample, nothing else)
+  fp32 : forward rel-L2 <= 1e-5 and max-abs/max <= 2e-5;
+         grad_value, grad_attn rel-L2 <= 1e-4 (atomic ordering);
+         grad_loc rel-L2 <= 1e-4 after masking samples within 1e-4 px of a pixel boundary
+         (d out / d loc is discontinuous there and floor() is precision dependent)
+  bf16 : value/grad_out rounded to bf16, fp32 arithmetic: forward rel-L2 <= 4e-3 (one bf16 rounding
+         of the output), grad_value rel-L2 <= 1e-2 (one bf16 rounding), grad_loc/grad_attn <= 1e-4
+         (fp32 outputs, masked as above)
+"""
+import ctypes
+
+import pytest
+import torch
+
+from conftest import golden_op_cases, load_golden
+from oracle import msda_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {
+    torch.float64: dict(fwd=1e-12, fwd_max=1e-11, gv=1e-12, ga=1e-12, gl=1e-11),
+    torch.float32: dict(fwd=1e-5, fwd_max=2e-5, gv=1e-4, ga=1e-4, gl=1e-4),
+    torch.bfloat16: dict(fwd=4e-3, fwd_max=2e-2, gv=1e-2, ga=1e-4, gl=1e-4),
+}
+
+
+@pytest.fixture(scope="module")
+def msda(cuda_device):
+    import monosowa_b200
+    return monosowa_b200
+
+
+def _levels(shapes):
+    sh = torch.as_tensor(shapes, dtype=torch.long)
+    return sh, torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+
+
+def run_ours(msda, value, sh, lsi, loc, attn, grad_out, step=64):
+    """forward + autograd backward through the reference-shaped API."""
+    dev = torch.device("cuda:0")
+    v = value.to(dev).requires_grad_(True)
+    l = loc.to(dev).requires_grad_(True)
+    a = attn.to(dev).requires_grad_(True)
+    out = msda.MSDeformAttnFunction.apply(v, sh.to(dev), lsi.to(dev), l, a, step)
+    out.backward(grad_out.to(dev).reshape(out.shape))
+    torch.cuda.synchronize()
+    return out.detach().cpu(), v.grad.cpu(), l.grad.cpu(), a.grad.cpu()
+
+
+def check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=""):
+    """Inputs are fp64 'master' tensors; they are rounded to the kernel dtypes first, and the fp64
+    oracle is evaluated on those rounded values."""
+    ct = torch.float64 if dtype == torch.float64 else torch.float32
+    v_k, g_k = value.to(dtype), grad_out.to(dtype)
+    l_k, a_k = loc.to(ct), attn.to(ct)
+    out, gv, gl, ga = run_ours(msda, v_k, sh, lsi, l_k, a_k, g_k)
+    assert out.dtype == dtype and gv.dtype == dtype and gl.dtype == ct and ga.dtype == ct
+    args = (v_k.double(), sh, lsi, l_k.double(), a_k.double())
+    ref_out = O.forward_c(*args)
+    ref_gv, ref_gl, ref_ga = O.backward_c(*args, g_k.double())
+    tol = TOL[dtype]
+    e = dict(fwd=O.rel_l2(out, ref_out), fwd_max=O.max_abs_over_max(out, ref_out),
+             gv=O.rel_l2(gv, ref_gv), ga=O.rel_l2(ga, ref_ga))
+    keep = ~O.pixel_boundary_mask(l_k, sh, eps_px=1e-4)
+    e["gl"] = O.rel_l2(gl[keep], ref_gl[keep])
+    bad = {k: (v, tol[k]) for k, v in e.items() if not v <= tol[k]}
+    assert not bad, f"{label} {dtype}: out of tolerance {bad}; all={e}; masked={int((~keep).sum()) // 2}"
+    return e
+
+
+# --------------------------------------------------------------------------------------------
+# 1. golden vectors from the reference's own ms_deform_attn_core_pytorch
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_op_cases())
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_golden_vectors(msda, name, dtype):
+    g = load_golden("op", name)
+    ct = dtype
+    out, gv, gl, ga = run_ours(msda, g["value"].to(dtype), g["shapes"], g["level_start_index"],
+                               g["loc"].to(ct), g["attn"].to(ct), g["grad_out"].to(dtype))
+    if dtype == torch.float64:
+        assert O.rel_l2(out, g["out64"]) < 1e-12
+        assert O.rel_l2(gv, g["grad_value"]) < 1e-12
+        assert O.rel_l2(ga, g["grad_attn"]) < 1e-12
+        assert O.rel_l2(gl, g["grad_loc"]) < 1e-11
+    else:
+        # inputs were rounded to fp32 -> compare with the golden at fp32 input-noise level
+        assert O.rel_l2(out, g["out64"]) < 5e-6
+        assert O.rel_l2(gv, g["grad_value"]) < 5e-6
+        assert O.rel_l2(ga, g["grad_attn"]) < 5e-6
+        keep = ~O.pixel_boundary_mask(g["loc"], g["shapes"], eps_px=1e-4)
+        assert O.rel_l2(gl[keep], g["grad_loc"][keep]) < 5e-5
+
+
+# --------------------------------------------------------------------------------------------
+# 2. the reference's own test contract (ops/test.py)
+# --------------------------------------------------------------------------------------------
+def _testpy_inputs(D, dtype, dev):
+    torch.manual_seed(3)                                                     # ops/test.py:28
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    sh, lsi = _levels([(6, 4), (3, 2)])
+    S = 30
+    value = (torch.rand(N, S, M, D) * 0.01).to(dev, dtype)
+    loc = torch.rand(N, Lq, M, L, P, 2).to(dev, dtype)
+    attn = torch.rand(N, Lq, M, L, P) + 1e-5
+    attn = (attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)).to(dev, dtype)
+    return value, sh.to(dev), lsi.to(dev), loc, attn
+
+
+def test_refcontract_forward_equal_with_pytorch_double(msda, cuda_device):
+    """ops/test.py:31-44 -- default allclose against the grid_sample path, fp64."""
+    value, sh, lsi, loc, attn = _testpy_inputs(2, torch.float64, cuda_device)
+    ref = O.core_grid_sample(value.cpu(), sh.cpu(), loc.cpu(), attn.cpu())
+    out = msda.MSDeformAttnFunction.apply(value, sh, lsi, loc, attn, 2).cpu()
+    assert torch.allclose(out, ref)
+
+
+def test_refcontract_forward_equal_with_pytorch_float(msda, cuda_device):
+    """ops/test.py:47-60 -- rtol 1e-2 / atol 1e-3, fp32."""
+    value, sh, lsi, loc, attn = _testpy_inputs(2, torch.float32, cuda_device)
+    ref = O.core_grid_sample(value.cpu(), sh.cpu(), loc.cpu(), attn.cpu())
+    out = msda.MSDeformAttnFunction.apply(value, sh, lsi, loc, attn, 2).cpu()
+    assert torch.allclose(out, ref, rtol=1e-2, atol=1e-3)
+    assert O.rel_l2(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("D", [30, 32, 64, 71])
+def test_refcontract_gradcheck_all_inputs(msda, cuda_device, D):
+    """ops/test.py:63-78 -- numerical gradient check in fp64 (all three differentiable inputs)."""
+    value, sh, lsi, loc, attn = _testpy_inputs(D, torch.float64, cuda_device)
+    value.requires_grad_(True); loc.requires_grad_(True); attn.requires_grad_(True)
+    assert torch.autograd.gradcheck(msda.MSDeformAttnFunction.apply, (value, sh, lsi, loc, attn, 2))
+
+
+@pytest.mark.parametrize("D", [1025, 2048, 3096])
+def test_refcontract_gradcheck_wide_channels(msda, cuda_device, D):
+    """ops/test.py:85 lists D up to 3096 (one per reference kernel branch).  A full numerical
+    Jacobian w.r.t. value is 6e4..2e5 forward calls, so: numerical check w.r.t. loc and attn (small),
+    and grad_value against the analytic C oracle."""
+    value, sh, lsi, loc, attn = _testpy_inputs(D, torch.float64, cuda_device)
+    loc.requires_grad_(True); attn.requires_grad_(True)
+    fn = lambda l, a: msda.MSDeformAttnFunction.apply(value, sh, lsi, l, a, 2)
+    assert torch.autograd.gradcheck(fn, (loc, attn))
+    g = torch.randn(1, 2, 2 * D, dtype=torch.float64)
+    _, gv, gl, ga = run_ours(msda, value.detach().cpu(), sh.cpu(), lsi.cpu(), loc.detach().cpu(), attn.detach().cpu(), g)
+    rgv, rgl, rga = O.backward_c(value.cpu(), sh.cpu(), lsi.cpu(), loc.detach().cpu(), attn.detach().cpu(), g)
+    assert O.rel_l2(gv, rgv) < 1e-12 and O.rel_l2(gl, rgl) < 1e-11 and O.rel_l2(ga, rga) < 1e-12
+
+
+# --------------------------------------------------------------------------------------------
+# 3. vector kernels vs the explicit-loop oracle: dtypes, D, ragged tails, out-of-range samples
+# --------------------------------------------------------------------------------------------
+def _random_case(seed, shapes, N, M, D, Lq, P, spread=2.32, shift=-0.66):
+    g = torch.Generator().manual_seed(seed)
+    sh, lsi = _levels(shapes)
+    S, L = int(sh.prod(1).sum()), len(shapes)
+    value = torch.randn(N, S, M, D, generator=g, dtype=torch.float64)
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g, dtype=torch.float64) * spread + shift
+    attn = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g, dtype=torch.float64), -1).view(N, Lq, M, L, P)
+    grad_out = torch.randn(N, Lq, M * D, generator=g, dtype=torch.float64)
+    return value, sh, lsi, loc, attn, grad_out
+
+
+VEC_CASES = [
+    # (shapes, N, M, D, Lq, P)
+    ([(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 131, 4),     # MonoDETR head layout, ragged Lq
+    ([(12, 40), (6, 20), (3, 10), (2, 5)], 1, 8, 32, 1, 4),       # a single query
+    ([(9, 7), (5, 4)], 3, 3, 32, 17, 4),                          # M not a power of two
+    ([(9, 7), (5, 4), (1, 1)], 2, 2, 16, 33, 4),
+    ([(9, 7), (5, 4)], 2, 4, 64, 19, 4),
+    ([(16, 16)], 1, 1, 32, 257, 4),                               # single level, many chunks
+    ([(9, 7), (5, 4)], 2, 4, 32, 19, 2),                          # P != 4 -> generic kernels
+    ([(9, 7), (5, 4)], 2, 4, 24, 19, 4),                          # D not vectorisable -> generic
+]
+
+
+@pytest.mark.parametrize("case", VEC_CASES, ids=lambda c: f"M{c[2]}D{c[3]}Lq{c[4]}P{c[5]}L{len(c[0])}")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
+def test_kernels_vs_oracle(msda, case, dtype):
+    shapes, N, M, D, Lq, P = case
+    value, sh, lsi, loc, attn, grad_out = _random_case(100 + D + Lq, shapes, N, M, D, Lq, P)
+    check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=str(case))
+
+
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("threads", [64, 128, 256, 512])
+def test_every_launch_variant_is_correct(msda, order, threads):
+    value, sh, lsi, loc, attn, grad_out = _random_case(7, [(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 203, 4)
+    L = msda._lib
+    try:
+        L.set_tuning("fwd_variant", order); L.set_tuning("bwd_variant", order); L.set_tuning("block_threads", threads)
+        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.float32, label=f"order{order} t{threads}")
+        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.bfloat16, label=f"order{order} t{threads}")
+    finally:
+        L.set_tuning("fwd_variant", -1); L.set_tuning("bwd_variant", -1); L.set_tuning("block_threads", -1)
+
+
+def test_generic_and_vector_kernels_agree(msda):
+    """variant 99 forces the generic kernels for a vectorisable shape."""
+    value, sh, lsi, loc, attn, grad_out = _random_case(8, [(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 77, 4)
+    L = msda._lib
+    a = run_ours(msda, value.float(), sh, lsi, loc.float(), attn.float(), grad_out.float())
+    try:
+        L.set_tuning("fwd_variant", 99); L.set_tuning("bwd_variant", 99)
+        b = run_ours(msda, value.float(), sh, lsi, loc.float(), attn.float(), grad_out.float())
+    finally:
+        L.set_tuning("fwd_variant", -1); L.set_tuning("bwd_variant", -1)
+    for x, y, tol in zip(a, b, (2e-6, 1e-5, 1e-5, 1e-5)):
+        assert O.rel_l2(x, y) < tol
+
+
+def test_edge_locations_exact_borders(msda):
+    g = load_golden("op", "d32_edges")
+    for dtype in (torch.float64, torch.float32):
+        check_against_oracle(msda, g["value"], g["shapes"], g["level_start_index"], g["loc"], g["attn"],
+                             g["grad_out"], dtype, label="edges")
+
+
+def test_all_samples_out_of_range(msda, cuda_device):
+    value, sh, lsi, loc, attn, grad_out = _random_case(9, [(5, 6), (3, 3)], 2, 8, 32, 21, 4)
+    loc = loc.abs() + 1.3                                            # everything beyond the right/bottom edge
+    out, gv, gl, ga = run_ours(msda, value.float(), sh, lsi, loc.float(), attn.float(), grad_out.float())
+    assert (out == 0).all() and (gv == 0).all() and (gl == 0).all() and (ga == 0).all()
+
+
+def test_empty_and_degenerate_shapes(msda, cuda_device):
+    sh, lsi = _levels([(4, 4), (2, 2)])
+    dev = cuda_device
+    value = torch.randn(2, 20, 8, 32, device=dev)
+    loc = torch.rand(2, 0, 8, 2, 4, 2, device=dev)
+    attn = torch.rand(2, 0, 8, 2, 4, device=dev)
+    v = value.clone().requires_grad_(True)
+    out = msda.MSDeformAttnFunction.apply(v, sh.to(dev), lsi.to(dev), loc, attn, 64)
+    assert out.shape == (2, 0, 256)
+    out.sum().backward()
+    assert (v.grad == 0).all()
+    # batch 0
+    out0 = msda.MSDeformAttnFunction.apply(value[:0], sh.to(dev), lsi.to(dev), torch.rand(0, 3, 8, 2, 4, 2, device=dev),
+                                           torch.rand(0, 3, 8, 2, 4, device=dev), 64)
+    assert out0.shape == (0, 3, 256)
+
+
+# --------------------------------------------------------------------------------------------
+# 4. full-size workloads (BASELINE.json configs)
+# --------------------------------------------------------------------------------------------
+def test_config0_shape_vs_oracle_f32(msda):
+    """configs[0] shape (batch 2, 10200 queries): full comparison, the oracle takes seconds."""
+    from monosowa_b200 import workloads as W
+    wl = W.config(0)
+    d = W.make_inputs(wl)
+    e = check_against_oracle(msda, d["value"].double(), d["shapes"], d["lsi"], d["loc"].double(),
+                             d["attn"].double(), d["grad_out"].double(), torch.float32, label=wl.name)
+    print("config0 errors", e)
+
+
+@pytest.mark.parametrize("mode", ["model", "uniform"])
+def test_config1_full_size_f32(msda, cuda_device, mode):
+    """configs[1] (the headline: batch 16, fp32).  Oracle comparison on one image of the batch plus
+    size-independent properties on the whole batch: linearity in value, the adjoint identity
+    <f(v), g> = <v, grad_value(g)>, <f(v; a'), g> = <a', grad_attn(g)>, bitwise-repeatable forward."""
+    from monosowa_b200 import workloads as W
+    wl = W.config(1, loc_mode=mode)
+    d = W.make_inputs(wl, device=cuda_device)
+    F = msda.MSDeformAttnFunction.apply
+    v = d["value"].requires_grad_(True); l = d["loc"].requires_grad_(True); a = d["attn"].requires_grad_(True)
+    out = F(v, d["shapes"], d["lsi"], l, a, 64)
+    out.backward(d["grad_out"])
+    # (a) one image against the fp64 oracle
+    i = 5
+    sl = lambda t: t[i:i + 1].detach().cpu().double()
+    ref_out = O.forward_c(sl(v), d["shapes"].cpu(), d["lsi"].cpu(), sl(l), sl(a))
+    rgv, rgl, rga = O.backward_c(sl(v), d["shapes"].cpu(), d["lsi"].cpu(), sl(l), sl(a), sl(d["grad_out"]))
+    assert O.rel_l2(out[i:i + 1], ref_out) < 1e-5
+    assert O.max_abs_over_max(out[i:i + 1], ref_out) < 2e-5
+    assert O.rel_l2(v.grad[i:i + 1], rgv) < 1e-4
+    assert O.rel_l2(a.grad[i:i + 1], rga) < 1e-4
+    keep = ~O.pixel_boundary_mask(sl(l), d["shapes"].cpu(), eps_px=1e-4)
+    assert O.rel_l2(l.grad[i:i + 1].cpu()[keep], rgl[keep]) < 1e-4
+    # (b) properties over the whole batch (fp64 accumulation of the inner products)
+    with torch.no_grad():
+        v2 = torch.randn_like(v)
+        o2 = F(v2, d["shapes"], d["lsi"], l, a, 64)
+        lin = F(2.5 * v - v2, d["shapes"], d["lsi"], l, a, 64)
+        assert O.rel_l2(lin, 2.5 * out - o2) < 1e-5
+        lhs = (o2.double() * d["grad_out"].double()).sum().item()
+        rhs = (v2.double() * v.grad.double()).sum().item()
+        scale = (o2.double().norm() * d["grad_out"].double().norm()).item()
+        assert abs(lhs - rhs) < 1e-5 * scale
+        a2 = torch.rand_like(a)
+        o3 = F(v, d["shapes"], d["lsi"], l, a2, 64)
+        lhs = (o3.double() * d["grad_out"].double()).sum().item()
+        rhs = (a2.double() * a.grad.double()).sum().item()
+        scale = (o3.double().norm() * d["grad_out"].double().norm()).item()
+        assert abs(lhs - rhs) < 1e-5 * scale
+        assert torch.equal(F(v, d["shapes"], d["lsi"], l, a, 64), out)
+
+
+@pytest.mark.parametrize("lq", [50, 550])
+def test_config2_decoder_bf16(msda, lq):
+    """configs[2]: decoder cross-attention, 50 (eval) / 550 (train) queries, bf16 value."""
+    from monosowa_b200 import workloads as W
+    wl = W.config(2, num_queries=lq, batch=4)
+    d = W.make_inputs(wl)
+    check_against_oracle(msda, d["value"].double(), d["shapes"], d["lsi"], d["loc"].double(), d["attn"].double(),
+                         d["grad_out"].double(), torch.bfloat16, label=wl.name)
+
+
+def test_config4_large_image_shapes(msda):
+    """configs[4] shapes (KITTI-360, Waymo 1280x1920, 640x960), batch 1, fp32 + bf16."""
+    from monosowa_b200 import workloads as W
+    for wl in W.sweep_config5(batch=1):
+        d = W.make_inputs(wl)
+        check_against_oracle(msda, d["value"].double(), d["shapes"], d["lsi"], d["loc"].double(),
+                             d["attn"].double(), d["grad_out"].double(), wl.dtype, label=wl.name)
+
+
+# --------------------------------------------------------------------------------------------
+# 5. against the reference's own CUDA kernels recompiled for sm_100a (oracle/_ref)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not O.ref_cuda_available(), reason="oracle/_ref not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_matches_reference_cuda_kernels(msda, cuda_device, dtype):
+    from monosowa_b200 import workloads as W
+    wl = W.config(0, batch=2, dtype=dtype)
+    d = W.make_inputs(wl, device=cuda_device)
+    ours = torch.ops.msda.forward(d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"], 64)
+    ref = O.ref_cuda_forward(d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"])
+    gv, gl, ga = torch.ops.msda.backward(d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"], d["grad_out"], 64)
+    rgv, rgl, rga = O.ref_cuda_backward(d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"], d["grad_out"])
+    torch.cuda.synchronize()
+    t = 1e-6 if dtype == torch.float32 else 1e-14
+    # identical fp32 floor() decisions by construction -> no boundary masking needed here
+    assert O.rel_l2(ours, ref) < t
+    assert O.rel_l2(gv, rgv) < 10 * t and O.rel_l2(gl, rgl) < 10 * t and O.rel_l2(ga, rga) < 10 * t
+
+
+# --------------------------------------------------------------------------------------------
+# 6. API / error behaviour / streams / graphs
+# --------------------------------------------------------------------------------------------
+def test_error_behaviour_matches_reference(msda, cuda_device):
+    value, sh, lsi, loc, attn, _ = _random_case(10, [(5, 6), (3, 3)], 4, 8, 32, 9, 4)
+    dev = cuda_device
+    v, l, a = value.float().to(dev), loc.float().to(dev), attn.float().to(dev)
+    sh, lsi = sh.to(dev), lsi.to(dev)
+    F = msda.MSDeformAttnFunction.apply
+    with pytest.raises(RuntimeError, match="contiguous"):                        # ms_deform_attn_cuda.cu:28
+        F(v.transpose(1, 2).contiguous().transpose(1, 2), sh, lsi, l, a, 64)
+    with pytest.raises(RuntimeError, match="im2col_step"):                       # ms_deform_attn_cuda.cu:52
+        F(v, sh, lsi, l, a, 3)
+    with pytest.raises(NotImplementedError):                                     # ms_deform_attn.h:38
+        F(v.cpu(), sh.cpu(), lsi.cpu(), l.cpu(), a.cpu(), 64)
+    with pytest.raises(RuntimeError):
+        F(v.half(), sh, lsi, l, a, 64)
+    with pytest.raises(RuntimeError, match="inconsistent"):
+        F(v, sh, lsi, l[:, :, :4].contiguous(), a, 64)
+    assert F(v, sh, lsi, l, a, 2).shape == (4, 9, 256)                           # 4 % 2 == 0 is fine
+
+
+def test_c_abi_direct_call_and_error_codes(msda, cuda_device):
+    """Call the exported symbols with raw pointers, as a non-Python host would."""
+    lib = msda._lib.lib
+    value, sh, lsi, loc, attn, _ = _random_case(11, [(5, 6), (3, 3)], 1, 8, 32, 9, 4)
+    dev = cuda_device
+    v, l, a = value.float().to(dev), loc.float().to(dev), attn.float().to(dev)
+    shd, lsid = sh.to(dev), lsi.to(dev)
+    out = torch.full((1, 9, 256), float("nan"), device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n0 = msda._lib.launch_count()
+    rc = lib.msda_forward_f32(p(v), p(shd), p(lsid), p(l), p(a), p(out), 1, 39, 8, 32, 2, 9, 4, st)
+    torch.cuda.synchronize()
+    assert rc == 0 and msda._lib.last_error() == "" and msda._lib.launch_count() == n0 + 1
+    ref = O.forward_c(v.cpu().double(), sh, lsi, l.cpu().double(), a.cpu().double())
+    assert O.rel_l2(out, ref) < 1e-5
+    assert lib.msda_forward_f32(None, p(shd), p(lsid), p(l), p(a), p(out), 1, 39, 8, 32, 2, 9, 4, st) == -1
+    assert "NULL" in msda._lib.last_error()
+    assert lib.msda_forward_f32(p(v), p(shd), p(lsid), p(l), p(a), p(out), 1, 39, 8, 32, 99, 9, 4, st) == -2
+    assert lib.msda_forward_f32(p(v), p(shd), p(lsid), p(l), p(a), p(out), -1, 39, 8, 32, 2, 9, 4, st) == -2
+    # a 4-byte-aligned but not 16-byte-aligned view must still work (generic kernels)
+    buf = torch.zeros(v.numel() + 1, device=dev)
+    buf[1:].copy_(v.flatten())
+    out2 = torch.empty_like(out)
+    rc = lib.msda_forward_f32(ctypes.c_void_p(buf.data_ptr() + 4), p(shd), p(lsid), p(l), p(a), p(out2),
+                              1, 39, 8, 32, 2, 9, 4, st)
+    torch.cuda.synchronize()
+    assert rc == 0 and O.rel_l2(out2, out) < 2e-6
+
+
+def test_side_stream_and_cuda_graph(msda, cuda_device):
+    from monosowa_b200 import workloads as W
+    d = W.make_inputs(W.config(0, batch=1), device=cuda_device)
+    args = (d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"])
+    want = torch.ops.msda.forward(*args, 64)
+    wgv, wgl, wga = torch.ops.msda.backward(*args, d["grad_out"], 64)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        got = torch.ops.msda.forward(*args, 64)
+    s.synchronize()
+    assert torch.equal(got, want)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):                        # no host sync / host metadata reads inside
+        g_out = torch.ops.msda.forward(*args, 64)
+        g_gv, g_gl, g_ga = torch.ops.msda.backward(*args, d["grad_out"], 64)
+    g_out.zero_(); g_gv.fill_(7.0)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(g_out, want)
+    assert O.rel_l2(g_gv, wgv) < 1e-5 and torch.equal(g_gl, wgl) and torch.equal(g_ga, wga)
+
+
+def test_registered_op_autograd_and_fake(msda, cuda_device):
+    value, sh, lsi, loc, attn, grad_out = _random_case(12, [(5, 6), (3, 3)], 2, 8, 32, 9, 4)
+    dev = cuda_device
+    v = value.float().to(dev).requires_grad_(True)
+    l = loc.float().to(dev).requires_grad_(True)
+    a = attn.float().to(dev).requires_grad_(True)
+    out = torch.ops.msda.forward(v, sh.to(dev), lsi.to(dev), l, a, 64)       # autograd registered on the op itself
+    out.backward(grad_out.float().to(dev))
+    ref = run_ours(msda, value.float(), sh, lsi, loc.float(), attn.float(), grad_out.float())
+    assert torch.equal(out.detach().cpu(), ref[0])
+    assert O.rel_l2(v.grad, ref[1]) < 1e-5 and torch.equal(l.grad.cpu(), ref[2]) and torch.equal(a.grad.cpu(), ref[3])
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        fv = torch.empty(2, 39, 8, 32, device="cuda")
+        fo = torch.ops.msda.forward(fv, torch.empty(2, 2, dtype=torch.long, device="cuda"),
+                                    torch.empty(2, dtype=torch.long, device="cuda"),
+                                    torch.empty(2, 9, 8, 2, 4, 2, device="cuda"), torch.empty(2, 9, 8, 2, 4, device="cuda"), 64)
+        assert fo.shape == (2, 9, 256)
+
+
+# --------------------------------------------------------------------------------------------
+# 7. the MSDeformAttn module against goldens produced by the reference module
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ref2", "ref6"])
+def test_module_matches_reference_module_golden(msda, cuda_device, name):
+    g = load_golden("module", name)
+    mod = msda.MSDeformAttn(d_model=g["d_model"], n_levels=g["shapes"].shape[0], n_heads=g["heads"],
+                            n_points=g["points"]).double()
+    state = {k[len("state__"):]: v for k, v in g.items() if k.startswith("state__")}
+    mod.load_state_dict(state, strict=True)
+    mod = mod.to(cuda_device)
+    dev = cuda_device
+    out = mod(g["query"].to(dev), g["ref"].to(dev), g["src"].to(dev), g["shapes"].to(dev),
+              g["level_start_index"].to(dev), g["mask"].to(dev))
+    assert O.rel_l2(out, g["out"]) < 1e-12
+    out32 = mod.float()(g["query"].float().to(dev), g["ref"].float().to(dev), g["src"].float().to(dev),
+                        g["shapes"].to(dev), g["level_start_index"].to(dev), g["mask"].to(dev))
+    assert O.rel_l2(out32, g["out"]) < 1e-5
+
+
+def test_module_bf16_autocast_trains(msda, cuda_device):
+    torch.manual_seed(0)
+    dev = cuda_device
+    sh, lsi = _levels([(12, 40), (6, 20), (3, 10), (2, 5)])
+    S = int(sh.prod(1).sum())
+    mod = msda.MSDeformAttn().to(dev)
+    q = torch.randn(2, S, 256, device=dev, requires_grad=True)
+    src = torch.randn(2, S, 256, device=dev, requires_grad=True)
+    from monosowa_b200.workloads import encoder_reference_points
+    ref = encoder_reference_points(sh.tolist(), dev)[None].expand(2, -1, -1, -1).contiguous()
+    out32 = mod(q, ref, src, sh.to(dev), lsi.to(dev))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out16 = mod(q, ref, src, sh.to(dev), lsi.to(dev))
+    assert out16.dtype == torch.bfloat16
+    assert O.rel_l2(out16.float(), out32) < 2e-2
+    out16.float().pow(2).mean().backward()
+    assert q.grad is not None and src.grad is not None and torch.isfinite(src.grad).all()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in mod.parameters())
