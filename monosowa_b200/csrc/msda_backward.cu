@@ -12,6 +12,7 @@
 //     (the reference: smem staging, 2 __syncthreads and a serial D-way sum per sample point);
 //   * level geometry is staged in shared memory once per CTA.
 #include "msda_common.cuh"
+#include "msda_records.cuh"
 
 namespace msda {
 
@@ -130,6 +131,107 @@ bwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
 }
 
 // ------------------------------------------------------------------------------------------------
+// record kernel (second generation, see msda_records.cuh).  Per batch of G samples:
+//   1. lane s of a lane group builds the geometry record of sample s (kept privately as well);
+//   2. every lane walks the G records: 4 corner loads of its 4 channels, 4 partial dot products
+//      t_ij = sum_c g_c * v_ij,c  and one REDG.E.ADD.F32x4 per contributing corner ((w_ij*a) * g);
+//   3. a butterfly reduce-scatter hands lane s the four totals t_ij of ITS sample; that lane turns
+//      them into grad_attn = sum w_ij t_ij and grad_loc = (W*a*(hy(t01-t00)+ly(t11-t10)),
+//      H*a*(hx(t10-t00)+lx(t11-t01)))  (ms_deform_im2col_cuda.cuh:119-158) and writes them,
+//      overwriting every element exactly once (zeros for outside samples, cuh:365-367).
+// ------------------------------------------------------------------------------------------------
+template <typename VT, int D, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
+               const int64_t *__restrict__ lsi, const float *__restrict__ loc,
+               const float *__restrict__ attn, const VT *__restrict__ grad_out,
+               float *__restrict__ grad_value, float *__restrict__ grad_loc,
+               float *__restrict__ grad_attn, const Dims d, const int order)
+{
+    constexpr int G = D / kChannelsPerLane;
+    using RL = RecordLayout<G>;
+    constexpr int QPW = RL::QPW;
+    static_assert(G >= 2 && G <= 32 && (32 % G) == 0, "unsupported D");
+
+    __shared__ LevelInfo s_lv[MSDA_MAX_LEVELS];
+    __shared__ __align__(16) uint32_t s_rec[8 * RL::WARP_WORDS];
+    stage_levels(s_lv, shapes, lsi, d.L);
+
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G, k = lane / G;
+    WorkItem w = decode_work<QPW>(d, order, k);
+    if (__ballot_sync(kFullMask, w.valid) == 0) return;
+    if (!w.valid) { w.n = 0; w.q = 0; w.m = 0; }
+
+    const int LP = d.L * d.P;
+    const long qm = ((long)w.n * d.Lq + w.q) * d.M + w.m;
+    const long img = ((long)w.n * d.S * d.M + w.m) * D + gl * kChannelsPerLane;
+    const VT *vimg = value + img;
+    float *gvimg = grad_value + img;
+    const int xs = d.M * D;
+    uint32_t *grp = s_rec + (threadIdx.x >> 5) * RL::WARP_WORDS + k * RL::GROUP_WORDS;
+
+    float g[4];
+    Vec4<VT>::load(grad_out + qm * D + gl * kChannelsPerLane, g);
+
+    SampleIn in = fetch_sample(w.valid && gl < LP, loc, attn, qm * LP + gl);
+    for (int b0 = 0; b0 < LP; b0 += G) {
+        const int sidx = b0 + gl;
+        const bool has = w.valid && sidx < LP;
+        const SampleGeom gm = build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, has && d.S > 0, in, s_lv,
+                                           sidx / d.P, xs);
+        __syncwarp();
+        in = fetch_sample(w.valid && sidx + G < LP, loc, attn, qm * LP + sidx + G);       // next batch, in flight
+
+        float t[4 * G];
+#pragma unroll
+        for (int s = 0; s < G; ++s) {
+            t[4 * s] = t[4 * s + 1] = t[4 * s + 2] = t[4 * s + 3] = 0.f;
+            const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
+            const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
+            if (d.S > 0) {
+                float v00[4], v01[4], v10[4], v11[4];
+                Vec4<VT>::load(vimg + off.x, v00);
+                Vec4<VT>::load(vimg + off.y, v01);
+                Vec4<VT>::load(vimg + off.z, v10);
+                Vec4<VT>::load(vimg + off.w, v11);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    t[4 * s] += g[c] * v00[c];
+                    t[4 * s + 1] += g[c] * v01[c];
+                    t[4 * s + 2] += g[c] * v10[c];
+                    t[4 * s + 3] += g[c] * v11[c];
+                }
+            }
+            // a zero weight contributes nothing to grad_value (corner outside the map, sample outside
+            // the window, a == 0, or an exactly integral coordinate): skip the reduction -- the
+            // SM->L2 reduction port is the scarce resource of this kernel
+            if (wa.x != 0.f) red_add_f32x4(gvimg + off.x, wa.x * g[0], wa.x * g[1], wa.x * g[2], wa.x * g[3]);
+            if (wa.y != 0.f) red_add_f32x4(gvimg + off.y, wa.y * g[0], wa.y * g[1], wa.y * g[2], wa.y * g[3]);
+            if (wa.z != 0.f) red_add_f32x4(gvimg + off.z, wa.z * g[0], wa.z * g[1], wa.z * g[2], wa.z * g[3]);
+            if (wa.w != 0.f) red_add_f32x4(gvimg + off.w, wa.w * g[0], wa.w * g[1], wa.w * g[2], wa.w * g[3]);
+        }
+        __syncwarp();
+
+        group_reduce_scatter<G, 4 * G>(t, gl);          // lane s now holds t00,t01,t10,t11 of sample s
+        if (has) {
+            float gx = 0.f, gy = 0.f, ga = 0.f;
+            if (gm.live) {
+                // corners outside the map were read from a clamped address; the reference counts 0
+                const float t00 = (gm.vmask & 1u) ? t[0] : 0.f, t01 = (gm.vmask & 2u) ? t[1] : 0.f;
+                const float t10 = (gm.vmask & 4u) ? t[2] : 0.f, t11 = (gm.vmask & 8u) ? t[3] : 0.f;
+                ga = gm.w00 * t00 + gm.w01 * t01 + gm.w10 * t10 + gm.w11 * t11;
+                gx = gm.Wf * gm.a * (gm.hy * (t01 - t00) + gm.ly * (t11 - t10));
+                gy = gm.Hf * gm.a * (gm.hx * (t10 - t00) + gm.lx * (t11 - t01));
+            }
+            const long si = qm * LP + sidx;
+            *reinterpret_cast<float2 *>(grad_loc + 2 * si) = make_float2(gx, gy);
+            grad_attn[si] = ga;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic kernel: one warp per (n, q, m); lanes stride over channels; any D / P / alignment.
 // VT value & grad_out type, CT arithmetic / loc / attn / all-gradients type.
 // ------------------------------------------------------------------------------------------------
@@ -217,11 +319,62 @@ constexpr bool vec_supported(int D, int P)
     return D == 32 || D == 64;
 }
 
+// Kernel choice (bwd_variant): -1 = measured default, 0/1 = vector kernel with work order 0/1,
+// 10/11 = record kernel with order 0/1, 99 = generic.
+// Default, measured on B200 at configs[1] (profiles/r01_v2_sweep.jsonl): the backward is bound by
+// the SM->L2 reduction port, not by instruction issue, so for fp32 the older vector kernel (64
+// registers, 4 CTAs/SM) still edges out the record kernel (80 registers, 3 CTAs/SM): 1.56 vs
+// 1.61 ms.  For bf16 the record kernel wins clearly (1.56 vs 2.77 ms) because its 8-lane groups
+// emit full 128-byte reduction lines.
 template <typename VT>
 bool use_vec(const Dims &d, bool vec_ok)
 {
-    return vec_ok && tuning().bwd_variant != 99 && vec_supported<VT>(d.D, d.P) &&
-           (long)d.S * d.M * d.D < (1L << 31);
+    const int v = tuning().bwd_variant;
+    const bool pick = (v == 0 || v == 1) || (v < 0 && sizeof(VT) == 4);
+    return vec_ok && pick && vec_supported<VT>(d.D, d.P) && (long)d.S * d.M * d.D < (1L << 31);
+}
+
+template <typename VT>
+bool use_rec(const Dims &d, bool vec_ok)
+{
+    const int v = tuning().bwd_variant;
+    const bool pick = (v == 10 || v == 11) || (v < 0 && !use_vec<VT>(d, vec_ok));
+    return vec_ok && pick && (d.D == 16 || d.D == 32 || d.D == 64) && (long)d.S * d.M * d.D < (1L << 31);
+}
+
+template <typename VT, int D>
+int run_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+            const void *attn, const void *grad_out, void *gv, void *gl, void *ga, const Dims &d,
+            cudaStream_t st)
+{
+    constexpr int QPW = 32 / (D / kChannelsPerLane);
+    const int threads = 256;                       // s_rec is sized for 8 warps
+    const int order = tuning().bwd_variant == 10 ? 0 : 1;
+    const long grid = grid_for(d, order, QPW, threads);
+    constexpr int MINB = D <= 32 ? 3 : 1;          // 3 CTAs/SM (<= 80 regs) for the MonoDETR head width
+    if (tuning().bwd_pipe == 1)
+        bwd_rec_kernel<VT, D, 1><<<(unsigned)grid, threads, 0, st>>>(
+            (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,
+            (float *)gv, (float *)gl, (float *)ga, d, order);
+    else
+        bwd_rec_kernel<VT, D, MINB><<<(unsigned)grid, threads, 0, st>>>(
+            (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,
+            (float *)gv, (float *)gl, (float *)ga, d, order);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+template <typename VT>
+int dispatch_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                 const void *attn, const void *grad_out, void *gv, void *gl, void *ga, const Dims &d,
+                 cudaStream_t st)
+{
+    switch (d.D) {
+    case 16: return run_rec<VT, 16>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st);
+    case 32: return run_rec<VT, 32>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st);
+    case 64: return run_rec<VT, 64>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st);
+    }
+    return (int)cudaErrorInvalidValue;
 }
 
 template <typename VT, int D, int P>
@@ -231,7 +384,7 @@ int run_vec(const void *value, const int64_t *shapes, const int64_t *lsi, const 
 {
     constexpr int QPW = 32 / (D / Vec<VT>::N);
     const int threads = tuning().block_threads > 0 ? tuning().block_threads : 256;
-    const int order = tuning().bwd_variant >= 0 ? tuning().bwd_variant : 1;
+    const int order = tuning().bwd_variant == 0 ? 0 : 1;
     const long grid = grid_for(d, order, QPW, threads);
     bwd_vec_kernel<VT, D, P><<<(unsigned)grid, threads, 0, st>>>(
         (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,
@@ -263,8 +416,11 @@ const char *backward_kernel_name(DType dt, int D, int L, int P, bool vec_ok)
     Dims d{1, 1, 1, D, 1, 1, P};
     switch (dt) {
     case DType::F64: return "bwd_generic_f64";
-    case DType::F32: return use_vec<float>(d, vec_ok) ? "bwd_vec_f32" : "bwd_generic_f32";
-    case DType::BF16: return use_vec<__nv_bfloat16>(d, vec_ok) ? "bwd_vec_bf16" : "bwd_generic_bf16";
+    case DType::F32:
+        return use_rec<float>(d, vec_ok) ? "bwd_rec_f32" : (use_vec<float>(d, vec_ok) ? "bwd_vec_f32" : "bwd_generic_f32");
+    case DType::BF16:
+        return use_rec<__nv_bfloat16>(d, vec_ok) ? "bwd_rec_bf16"
+                                                 : (use_vec<__nv_bfloat16>(d, vec_ok) ? "bwd_vec_bf16" : "bwd_generic_bf16");
     }
     return "?";
 }
@@ -282,6 +438,8 @@ int launch_backward(DType dt, const void *value, const int64_t *shapes, const in
     if ((long)d.N * d.Lq * d.M == 0) return 0;
 #define ARGS value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st
     if (dt == DType::F64) return run_generic<double, double>(ARGS);
+    if (dt == DType::F32 && use_rec<float>(d, vec_ok)) return dispatch_rec<float>(ARGS);
+    if (dt == DType::BF16 && use_rec<__nv_bfloat16>(d, vec_ok)) return dispatch_rec<__nv_bfloat16>(ARGS);
     if (dt == DType::F32) {
         if (use_vec<float>(d, vec_ok)) {
             switch (d.D) {

@@ -149,6 +149,8 @@ static int *tuning_slot(const char *key)
     if (!strcmp(key, "fwd_variant")) return &tuning().fwd_variant;
     if (!strcmp(key, "bwd_variant")) return &tuning().bwd_variant;
     if (!strcmp(key, "block_threads")) return &tuning().block_threads;
+    if (!strcmp(key, "fwd_pipe")) return &tuning().fwd_pipe;
+    if (!strcmp(key, "bwd_pipe")) return &tuning().bwd_pipe;
     return nullptr;
 }
 

@@ -233,6 +233,8 @@ struct Tuning {
     int fwd_variant = -1;
     int bwd_variant = -1;
     int block_threads = -1;
+    int fwd_pipe = -1;
+    int bwd_pipe = -1;
 };
 Tuning &tuning();
 void count_launch(int n = 1);

@@ -13,6 +13,7 @@
 //     level geometry comes from shared memory, all P points of a level are in flight together.
 // The op is a gather: no tensor cores, the bound is L1/L2 gather bandwidth.
 #include "msda_common.cuh"
+#include "msda_records.cuh"
 
 namespace msda {
 
@@ -100,6 +101,88 @@ fwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
 }
 
 // ------------------------------------------------------------------------------------------------
+// record kernel (second generation, see msda_records.cuh): geometry computed once per sample by
+// one lane, shared through shared memory; any L and P; D in {16, 32, 64}; fp32 or bf16 values.
+// ------------------------------------------------------------------------------------------------
+template <typename VT, int D, int PIPE>
+__global__ void __launch_bounds__(256)
+fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
+               const int64_t *__restrict__ lsi, const float *__restrict__ loc,
+               const float *__restrict__ attn, VT *__restrict__ out, const Dims d, const int order)
+{
+    constexpr int G = D / kChannelsPerLane;
+    using RL = RecordLayout<G>;
+    constexpr int QPW = RL::QPW;
+    static_assert(G >= 2 && G <= 32 && (32 % G) == 0, "unsupported D");
+
+    __shared__ LevelInfo s_lv[MSDA_MAX_LEVELS];
+    __shared__ __align__(16) uint32_t s_rec[8 * RL::WARP_WORDS];
+    stage_levels(s_lv, shapes, lsi, d.L);
+
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G, k = lane / G;
+    WorkItem w = decode_work<QPW>(d, order, k);
+    if (__ballot_sync(kFullMask, w.valid) == 0) return;
+    if (!w.valid) { w.n = 0; w.q = 0; w.m = 0; }
+
+    const int LP = d.L * d.P;
+    const long qm = ((long)w.n * d.Lq + w.q) * d.M + w.m;
+    const VT *vimg = value + ((long)w.n * d.S * d.M + w.m) * D + gl * kChannelsPerLane;
+    const int xs = d.M * D;
+    uint32_t *grp = s_rec + (threadIdx.x >> 5) * RL::WARP_WORDS + k * RL::GROUP_WORDS;
+
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (d.S > 0) {
+        SampleIn in = fetch_sample(w.valid && gl < LP, loc, attn, qm * LP + gl);
+        for (int b0 = 0; b0 < LP; b0 += G) {
+            const int sidx = b0 + gl;
+            build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, w.valid && sidx < LP, in, s_lv, sidx / d.P, xs);
+            __syncwarp();
+            in = fetch_sample(w.valid && sidx + G < LP, loc, attn, qm * LP + sidx + G);   // next batch, in flight
+            if constexpr (PIPE == 1) {
+#pragma unroll
+                for (int s = 0; s < G; ++s) {
+                    const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
+                    const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
+                    float v00[4], v01[4], v10[4], v11[4];
+                    Vec4<VT>::load(vimg + off.x, v00);
+                    Vec4<VT>::load(vimg + off.y, v01);
+                    Vec4<VT>::load(vimg + off.z, v10);
+                    Vec4<VT>::load(vimg + off.w, v11);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
+                }
+            } else {
+                // PIPE samples' corner loads are issued before the first of them is consumed
+#pragma unroll
+                for (int s0 = 0; s0 < G; s0 += PIPE) {
+                    float v[PIPE][4][4];
+                    float4 wa[PIPE];
+#pragma unroll
+                    for (int u = 0; u < PIPE; ++u) {
+                        const int4 off = *reinterpret_cast<const int4 *>(grp + (s0 + u) * 4);
+                        wa[u] = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + (s0 + u) * 4);
+                        Vec4<VT>::load(vimg + off.x, v[u][0]);
+                        Vec4<VT>::load(vimg + off.y, v[u][1]);
+                        Vec4<VT>::load(vimg + off.z, v[u][2]);
+                        Vec4<VT>::load(vimg + off.w, v[u][3]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < PIPE; ++u)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            acc[c] += wa[u].x * v[u][0][c] + wa[u].y * v[u][1][c] + wa[u].z * v[u][2][c] +
+                                      wa[u].w * v[u][3][c];
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (w.valid) Vec4<VT>::store(out + qm * D + gl * kChannelsPerLane, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic kernel: any D / P / alignment; VT value type, CT coordinate + arithmetic type.
 // One thread per output element, 64-bit indexing throughout.
 // ------------------------------------------------------------------------------------------------
@@ -184,12 +267,50 @@ int run_vec(const VT *value, const int64_t *shapes, const int64_t *lsi, const fl
 {
     constexpr int QPW = 32 / (D / Vec<VT>::N);
     const int threads = tuning().block_threads > 0 ? tuning().block_threads : 256;
-    const int order = tuning().fwd_variant >= 0 ? tuning().fwd_variant : 1;
+    const int order = tuning().fwd_variant == 0 ? 0 : 1;
     const long grid = grid_for(d, order, QPW, threads);
     fwd_vec_kernel<VT, D, P><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order);
     count_launch();
     return (int)cudaGetLastError();
 }
+
+template <typename VT, int D>
+int run_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
+            const float *attn, VT *out, const Dims &d, int order, cudaStream_t st)
+{
+    constexpr int QPW = 32 / (D / kChannelsPerLane);
+    const int threads = 256;                       // s_rec is sized for 8 warps
+    const long grid = grid_for(d, order, QPW, threads);
+    const int pipe = tuning().fwd_pipe > 0 ? tuning().fwd_pipe : 2;
+    if (pipe == 1)
+        fwd_rec_kernel<VT, D, 1><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order);
+    else if (pipe == 2)
+        fwd_rec_kernel<VT, D, 2><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order);
+    else
+        fwd_rec_kernel<VT, D, 4><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+template <typename VT>
+int dispatch_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                 const void *attn, void *out, const Dims &d, int order, cudaStream_t st)
+{
+    const VT *v = (const VT *)value;
+    const float *lo = (const float *)loc, *at = (const float *)attn;
+    VT *o = (VT *)out;
+    switch (d.D) {
+    case 16: return run_rec<VT, 16>(v, shapes, lsi, lo, at, o, d, order, st);
+    case 32: return run_rec<VT, 32>(v, shapes, lsi, lo, at, o, d, order, st);
+    case 64: return run_rec<VT, 64>(v, shapes, lsi, lo, at, o, d, order, st);
+    }
+    return (int)cudaErrorInvalidValue;
+}
+
+// variant: -1 default (records, order 1); 0/1 first-generation vector kernel with order 0/1;
+// 10/11 record kernel with order 0/1; 99 generic.
+inline bool rec_supported(const Dims &d) { return d.D == 16 || d.D == 32 || d.D == 64; }
+inline bool want_rec(int variant) { return variant < 0 || variant == 10 || variant == 11; }
 
 template <typename VT, typename CT>
 int run_generic(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
@@ -207,8 +328,13 @@ int run_generic(const void *value, const int64_t *shapes, const int64_t *lsi, co
 template <typename VT>
 bool use_vec(const Dims &d, bool vec_ok)
 {
-    return vec_ok && tuning().fwd_variant != 99 && vec_supported<VT>(d.D, d.P) &&
-           (long)d.S * d.M * d.D < (1L << 31);
+    const int v = tuning().fwd_variant;
+    return vec_ok && (v == 0 || v == 1) && vec_supported<VT>(d.D, d.P) && (long)d.S * d.M * d.D < (1L << 31);
+}
+
+bool use_rec(const Dims &d, bool vec_ok)
+{
+    return vec_ok && want_rec(tuning().fwd_variant) && rec_supported(d) && (long)d.S * d.M * d.D < (1L << 31);
 }
 
 }  // namespace
@@ -219,8 +345,10 @@ const char *forward_kernel_name(DType dt, int D, int L, int P, bool vec_ok)
     Dims d{1, 1, 1, D, 1, 1, P};
     switch (dt) {
     case DType::F64: return "fwd_generic_f64";
-    case DType::F32: return use_vec<float>(d, vec_ok) ? "fwd_vec_f32" : "fwd_generic_f32";
-    case DType::BF16: return use_vec<__nv_bfloat16>(d, vec_ok) ? "fwd_vec_bf16" : "fwd_generic_bf16";
+    case DType::F32:
+        return use_rec(d, vec_ok) ? "fwd_rec_f32" : (use_vec<float>(d, vec_ok) ? "fwd_vec_f32" : "fwd_generic_f32");
+    case DType::BF16:
+        return use_rec(d, vec_ok) ? "fwd_rec_bf16" : (use_vec<__nv_bfloat16>(d, vec_ok) ? "fwd_vec_bf16" : "fwd_generic_bf16");
     }
     return "?";
 }
@@ -230,6 +358,10 @@ int launch_forward(DType dt, const void *value, const int64_t *shapes, const int
                    cudaStream_t st)
 {
     if (dt == DType::F64) return run_generic<double, double>(value, shapes, lsi, loc, attn, out, d, st);
+    const int rec_order = tuning().fwd_variant == 10 ? 0 : 1;
+    if (dt == DType::F32 && use_rec(d, vec_ok)) return dispatch_rec<float>(value, shapes, lsi, loc, attn, out, d, rec_order, st);
+    if (dt == DType::BF16 && use_rec(d, vec_ok))
+        return dispatch_rec<__nv_bfloat16>(value, shapes, lsi, loc, attn, out, d, rec_order, st);
     if (dt == DType::F32) {
         if (use_vec<float>(d, vec_ok)) {
             const float *v = (const float *)value, *lo = (const float *)loc, *at = (const float *)attn;

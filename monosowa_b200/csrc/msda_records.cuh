@@ -1,0 +1,142 @@
+// msda_records.cuh -- "shared geometry" building blocks of the second-generation kernels.
+//
+// Measured on B200 (profiles/r01_v1_ncu_full_summary.md): the first-generation vector kernels
+// were instruction-issue bound -- every one of the G lanes that cover a (query, head) recomputed
+// the same bilinear geometry (coordinate, floor, validity, weights, four addresses) for each of
+// the L*P samples.  Here each lane of a lane group computes the geometry of ONE sample, drops a
+// 32-byte record into shared memory, and all G lanes then consume the G records of their group
+// with two broadcast LDS.128 per sample:
+//     record = { int32 element offset of the 4 corners (clamped into the map), 4 weights }
+// Consumption is branch-free so that all 4*G corner loads of a batch can be in flight together:
+//   * an invalid corner keeps a clamped (in-map) address and a zero weight -- the clamped pixel is
+//     always one of the sample's own valid corners;
+//   * a sample outside the (-1,H)x(-1,W) window, or past L*P, points at element 0 of the image
+//     (one hot L1 line) with four zero weights.
+// For finite `value` this is exactly the reference's skip logic (ms_deform_im2col_cuda.cuh:56-80,
+// 288); a NaN/Inf stored at pixel 0 of a head would additionally reach queries that have outside
+// samples (0 * NaN), which the reference's branches avoid -- documented in DESIGN.md.
+#pragma once
+
+#include "msda_common.cuh"
+
+namespace msda {
+
+constexpr int kChannelsPerLane = 4;
+
+// ---- 4-channel vectors: fp32 = 16-byte, bf16 = 8-byte accesses ------------------------------
+template <typename VT>
+struct Vec4;
+
+template <>
+struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float *p, float (&f)[4])
+    {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&f)[4])
+    {
+        *reinterpret_cast<float4 *>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+};
+
+template <>
+struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&f)[4])
+    {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        f[0] = __uint_as_float(v.x << 16);
+        f[1] = __uint_as_float(v.x & 0xffff0000u);
+        f[2] = __uint_as_float(v.y << 16);
+        f[3] = __uint_as_float(v.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&f)[4])
+    {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
+        const __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
+        *reinterpret_cast<uint2 *>(p) =
+            make_uint2(*reinterpret_cast<const unsigned *>(&a), *reinterpret_cast<const unsigned *>(&b));
+    }
+};
+
+// ---- per-warp record area --------------------------------------------------------------------
+// Group k (of QPW = 32/G groups) owns G records, stored as G int4 offsets followed by G float4
+// weights (so that the G lanes write 16-byte items at a 16-byte stride: conflict-free STS.128);
+// groups are 4 words apart modulo the 32 banks so that the broadcast reads of the QPW groups
+// never collide.
+template <int G>
+struct RecordLayout {
+    static constexpr int QPW = 32 / G;
+    static constexpr int GROUP_WORDS = G * 8 + 4;
+    static constexpr int WARP_WORDS = QPW * GROUP_WORDS;
+    static constexpr int WEIGHTS = G * 4;              // word offset of the weights inside a group
+};
+
+// What the owning lane keeps privately about its sample (needed again by the backward).
+struct SampleGeom {
+    float w00, w01, w10, w11;   // bilinear weights, zero for invalid corners
+    float hy, ly, hx, lx;
+    float a;                    // attention weight
+    float Wf, Hf;
+    unsigned vmask;             // bit0..3: corner 00, 01, 10, 11 lies inside the map
+    bool live;                  // sample exists (index < L*P, query valid) and is inside the window
+};
+
+// The raw inputs of one sample, fetched ahead of use (the next batch's are in flight while the
+// current batch is consumed).
+struct SampleIn {
+    float x, y, a;
+};
+
+__device__ __forceinline__ SampleIn fetch_sample(bool has, const float *__restrict__ loc,
+                                                 const float *__restrict__ attn, long sample_index)
+{
+    SampleIn in{0.f, 0.f, 0.f};
+    if (has) {
+        const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + sample_index);
+        in.x = xy.x; in.y = xy.y;
+        in.a = __ldg(attn + sample_index);
+    }
+    return in;
+}
+
+// Build the record of one sample and write it to `rec_off` / `rec_w` (16-byte aligned).  The
+// weights stored are w_ij * a (what both forward and grad_value need).
+__device__ __forceinline__ SampleGeom build_record(uint32_t *rec_off, uint32_t *rec_w, bool has, const SampleIn in,
+                                                   const LevelInfo *s_lv, int l, int xs)
+{
+    SampleGeom gm;
+    gm.live = false;
+    gm.w00 = gm.w01 = gm.w10 = gm.w11 = 0.f;
+    gm.hy = gm.ly = gm.hx = gm.lx = 0.f;
+    gm.a = 0.f; gm.Wf = 0.f; gm.Hf = 0.f; gm.vmask = 0u;
+    int4 off = make_int4(0, 0, 0, 0);
+    float4 wa = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has) {
+        const float a = in.a;
+        const LevelInfo li = s_lv[l];
+        const Tap<float> t = make_tap(in.x, in.y, li.H, li.W);
+        if (t.inside) {
+            const bool y0ok = t.y0 >= 0, y1ok = t.y0 + 1 <= li.H - 1;
+            const bool x0ok = t.x0 >= 0, x1ok = t.x0 + 1 <= li.W - 1;
+            const int y0c = max(t.y0, 0), y1c = min(t.y0 + 1, li.H - 1);
+            const int x0c = max(t.x0, 0), x1c = min(t.x0 + 1, li.W - 1);
+            gm.hy = 1.f - t.ly; gm.ly = t.ly; gm.hx = 1.f - t.lx; gm.lx = t.lx;
+            const float wy0 = y0ok ? gm.hy : 0.f, wy1 = y1ok ? gm.ly : 0.f;
+            const float wx0 = x0ok ? gm.hx : 0.f, wx1 = x1ok ? gm.lx : 0.f;
+            gm.w00 = wy0 * wx0; gm.w01 = wy0 * wx1; gm.w10 = wy1 * wx0; gm.w11 = wy1 * wx1;
+            gm.a = a; gm.Wf = (float)li.W; gm.Hf = (float)li.H;
+            gm.vmask = (y0ok && x0ok ? 1u : 0u) | (y0ok && x1ok ? 2u : 0u) | (y1ok && x0ok ? 4u : 0u) |
+                       (y1ok && x1ok ? 8u : 0u);
+            gm.live = true;
+            const int r0 = (li.start + y0c * li.W) * xs, r1 = (li.start + y1c * li.W) * xs;
+            off = make_int4(r0 + x0c * xs, r0 + x1c * xs, r1 + x0c * xs, r1 + x1c * xs);
+            wa = make_float4(gm.w00 * a, gm.w01 * a, gm.w10 * a, gm.w11 * a);
+        }
+    }
+    *reinterpret_cast<int4 *>(rec_off) = off;
+    *reinterpret_cast<float4 *>(rec_w) = wa;
+    return gm;
+}
+
+}  // namespace msda

@@ -174,7 +174,10 @@ VEC_CASES = [
     ([(9, 7), (5, 4), (1, 1)], 2, 2, 16, 33, 4),
     ([(9, 7), (5, 4)], 2, 4, 64, 19, 4),
     ([(16, 16)], 1, 1, 32, 257, 4),                               # single level, many chunks
-    ([(9, 7), (5, 4)], 2, 4, 32, 19, 2),                          # P != 4 -> generic kernels
+    ([(9, 7), (5, 4)], 2, 4, 32, 19, 2),                          # L*P = 4 < lanes per group
+    ([(9, 7), (5, 4), (3, 3)], 2, 4, 32, 19, 3),                  # L*P = 9: ragged last batch
+    ([(9, 7), (5, 4), (3, 3)], 1, 2, 64, 5, 5),                   # L*P = 15 with 16-lane groups
+    ([(9, 7), (5, 4)], 2, 4, 16, 21, 8),                          # L*P = 16 with 4-lane groups
     ([(9, 7), (5, 4)], 2, 4, 24, 19, 4),                          # D not vectorisable -> generic
 ]
 
@@ -187,7 +190,7 @@ def test_kernels_vs_oracle(msda, case, dtype):
     check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=str(case))
 
 
-@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("order", [0, 1, 10, 11])
 @pytest.mark.parametrize("threads", [64, 128, 256, 512])
 def test_every_launch_variant_is_correct(msda, order, threads):
     value, sh, lsi, loc, attn, grad_out = _random_case(7, [(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 203, 4)
