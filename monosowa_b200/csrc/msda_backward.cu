@@ -351,15 +351,18 @@ int run_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const 
     const int threads = 256;                       // s_rec is sized for 8 warps
     const int order = tuning().bwd_variant == 10 ? 0 : 1;
     const long grid = grid_for(d, order, QPW, threads);
-    constexpr int MINB = D <= 32 ? 3 : 1;          // 3 CTAs/SM (<= 80 regs) for the MonoDETR head width
-    if (tuning().bwd_pipe == 1)
-        bwd_rec_kernel<VT, D, 1><<<(unsigned)grid, threads, 0, st>>>(
-            (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,
-            (float *)gv, (float *)gl, (float *)ga, d, order);
-    else
-        bwd_rec_kernel<VT, D, MINB><<<(unsigned)grid, threads, 0, st>>>(
-            (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,
-            (float *)gv, (float *)gl, (float *)ga, d, order);
+    // bwd_pipe = requested minimum CTAs/SM (register cap 64K / (256 * MINB)); trades ILP for TLP
+#define MSDA_BWD_REC(MINB)                                                                                  \
+    bwd_rec_kernel<VT, D, MINB><<<(unsigned)grid, threads, 0, st>>>(                                        \
+        (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,      \
+        (float *)gv, (float *)gl, (float *)ga, d, order)
+    switch (tuning().bwd_pipe) {
+    case 1: MSDA_BWD_REC(1); break;
+    case 2: MSDA_BWD_REC(2); break;
+    case 4: MSDA_BWD_REC(4); break;
+    default: if (D <= 32) MSDA_BWD_REC(3); else MSDA_BWD_REC(1); break;
+    }
+#undef MSDA_BWD_REC
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -104,8 +104,8 @@ fwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
 // record kernel (second generation, see msda_records.cuh): geometry computed once per sample by
 // one lane, shared through shared memory; any L and P; D in {16, 32, 64}; fp32 or bf16 values.
 // ------------------------------------------------------------------------------------------------
-template <typename VT, int D, int PIPE>
-__global__ void __launch_bounds__(256)
+template <typename VT, int D, int MINB, bool COMPACT>
+__global__ void __launch_bounds__(256, MINB)
 fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                const float *__restrict__ attn, VT *__restrict__ out, const Dims d, const int order)
@@ -136,12 +136,21 @@ fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
         SampleIn in = fetch_sample(w.valid && gl < LP, loc, attn, qm * LP + gl);
         for (int b0 = 0; b0 < LP; b0 += G) {
             const int sidx = b0 + gl;
-            build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, w.valid && sidx < LP, in, s_lv, sidx / d.P, xs);
-            __syncwarp();
-            in = fetch_sample(w.valid && sidx + G < LP, loc, attn, qm * LP + sidx + G);   // next batch, in flight
-            if constexpr (PIPE == 1) {
-#pragma unroll
-                for (int s = 0; s < G; ++s) {
+            if constexpr (COMPACT) {
+                // live records only, packed to the front of the group's area: samples outside the
+                // window cost neither loads nor FMAs (15 % of them at MonoDETR's shapes)
+                __align__(16) uint32_t tmp[8];
+                const SampleGeom gm = build_record(tmp, tmp + 4, w.valid && sidx < LP, in, s_lv, sidx / d.P, xs);
+                const unsigned gmask = (__ballot_sync(kFullMask, gm.live) >> (k * G)) & ((G == 32) ? ~0u : ((1u << G) - 1u));
+                const int slot = __popc(gmask & ((1u << gl) - 1u));
+                const int cnt = __popc(gmask);
+                if (gm.live) {
+                    *reinterpret_cast<int4 *>(grp + slot * 4) = *reinterpret_cast<const int4 *>(tmp);
+                    *reinterpret_cast<float4 *>(grp + RL::WEIGHTS + slot * 4) = *reinterpret_cast<const float4 *>(tmp + 4);
+                }
+                __syncwarp();
+                in = fetch_sample(w.valid && sidx + G < LP, loc, attn, qm * LP + sidx + G);
+                for (int s = 0; s < cnt; ++s) {
                     const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
                     const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
                     float v00[4], v01[4], v10[4], v11[4];
@@ -153,28 +162,24 @@ fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                     for (int c = 0; c < 4; ++c)
                         acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
                 }
-            } else {
-                // PIPE samples' corner loads are issued before the first of them is consumed
+                __syncwarp();
+                continue;
+            }
+            build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, w.valid && sidx < LP, in, s_lv, sidx / d.P, xs);
+            __syncwarp();
+            in = fetch_sample(w.valid && sidx + G < LP, loc, attn, qm * LP + sidx + G);   // next batch, in flight
 #pragma unroll
-                for (int s0 = 0; s0 < G; s0 += PIPE) {
-                    float v[PIPE][4][4];
-                    float4 wa[PIPE];
+            for (int s = 0; s < G; ++s) {
+                const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
+                const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
+                float v00[4], v01[4], v10[4], v11[4];
+                Vec4<VT>::load(vimg + off.x, v00);
+                Vec4<VT>::load(vimg + off.y, v01);
+                Vec4<VT>::load(vimg + off.z, v10);
+                Vec4<VT>::load(vimg + off.w, v11);
 #pragma unroll
-                    for (int u = 0; u < PIPE; ++u) {
-                        const int4 off = *reinterpret_cast<const int4 *>(grp + (s0 + u) * 4);
-                        wa[u] = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + (s0 + u) * 4);
-                        Vec4<VT>::load(vimg + off.x, v[u][0]);
-                        Vec4<VT>::load(vimg + off.y, v[u][1]);
-                        Vec4<VT>::load(vimg + off.z, v[u][2]);
-                        Vec4<VT>::load(vimg + off.w, v[u][3]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < PIPE; ++u)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            acc[c] += wa[u].x * v[u][0][c] + wa[u].y * v[u][1][c] + wa[u].z * v[u][2][c] +
-                                      wa[u].w * v[u][3][c];
-                }
+                for (int c = 0; c < 4; ++c)
+                    acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
             }
             __syncwarp();
         }
@@ -281,13 +286,24 @@ int run_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const fl
     constexpr int QPW = 32 / (D / kChannelsPerLane);
     const int threads = 256;                       // s_rec is sized for 8 warps
     const long grid = grid_for(d, order, QPW, threads);
-    const int pipe = tuning().fwd_pipe > 0 ? tuning().fwd_pipe : 2;
-    if (pipe == 1)
-        fwd_rec_kernel<VT, D, 1><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order);
-    else if (pipe == 2)
-        fwd_rec_kernel<VT, D, 2><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order);
-    else
-        fwd_rec_kernel<VT, D, 4><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order);
+    // fwd_pipe = requested minimum CTAs/SM (register cap 64K / (256 * MINB)); trades ILP for TLP
+#define MSDA_FWD_REC(MINB, COMPACT) \
+    fwd_rec_kernel<VT, D, MINB, COMPACT><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order)
+    // Default, measured on B200 at configs[1] (profiles/r01_v2_compact_sweep.jsonl): fp32 -- compacting
+    // loop at <= 48 registers (5 CTAs/SM) 0.593 ms; bf16 -- unrolled loop at <= 40 registers 0.493 ms.
+    // All flavours sit within ~5 % of each other: the kernel is bound by L1 data-pipe wavefronts.
+    int flavour = tuning().fwd_pipe;
+    if (flavour < 0) flavour = sizeof(VT) == 4 ? 15 : 6;
+    switch (flavour) {
+    case 3: MSDA_FWD_REC(3, false); break;
+    case 5: MSDA_FWD_REC(5, false); break;
+    case 6: MSDA_FWD_REC(6, false); break;
+    case 15: MSDA_FWD_REC(5, true); break;
+    case 14: MSDA_FWD_REC(4, true); break;
+    case 16: MSDA_FWD_REC(6, true); break;
+    default: MSDA_FWD_REC(4, false); break;
+    }
+#undef MSDA_FWD_REC
     count_launch();
     return (int)cudaGetLastError();
 }
