@@ -77,6 +77,27 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+class _on_device:
+    """Make `dev` current for the launch; free when it already is (the common case)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev):
+        self.idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(self.idx))
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def _raise(rc, what):
     raise RuntimeError(f"{what} failed (code {rc}): {_lib.last_error()}")
 
@@ -87,9 +108,9 @@ def _forward_cuda(value, spatial_shapes, level_start_index, sampling_locations, 
     loc, attn = _as_coord(sampling_locations, value), _as_coord(attention_weights, value)
     out = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
     fn = getattr(_lib.lib, "msda_forward_" + _SUFFIX[value.dtype])
-    with torch.cuda.device(value.device):
+    with _on_device(value.device) as stream:
         rc = fn(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(loc), _ptr(attn), _ptr(out),
-                n, s, m, d, nl, lq, p, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                n, s, m, d, nl, lq, p, stream)
     if rc:
         _raise(rc, "msda::forward")
     return out
@@ -110,10 +131,10 @@ def _backward_cuda(value, spatial_shapes, level_start_index, sampling_locations,
     grad_loc = torch.empty(loc.shape, dtype=ct, device=value.device)
     grad_attn = torch.empty(attn.shape, dtype=ct, device=value.device)
     fn = getattr(_lib.lib, "msda_backward_" + _SUFFIX[value.dtype])
-    with torch.cuda.device(value.device):
+    with _on_device(value.device) as stream:
         rc = fn(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(loc), _ptr(attn),
                 _ptr(grad_output), _ptr(grad_value), _ptr(grad_loc), _ptr(grad_attn),
-                n, s, m, d, nl, lq, p, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                n, s, m, d, nl, lq, p, stream)
     if rc:
         _raise(rc, "msda::backward")
     if grad_value.dtype != value.dtype:                       # bf16: fp32 accumulation, narrowed once
