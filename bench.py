@@ -186,6 +186,8 @@ def run_ours(args, wl):
     from monosowa_b200 import workloads as W
     use_dist = world > 1
     if use_dist:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # keeps stdout to the one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 

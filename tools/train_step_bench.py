@@ -1,0 +1,221 @@
+#!/usr/bin/env python
+"""MonoDETR training-step benchmark (BASELINE.json configs[3]).
+
+Drives the UNMODIFIED reference model + criterion + optimizer (staged by tools/stage_reference.py
+into git-ignored baseline/_ref/MonoDETR) with this repo's MSDA op swapped in, on synthetic
+KITTI-shaped batches, data-parallel with DistributedDataParallel (NCCL) when launched by torchrun.
+
+    python tools/train_step_bench.py --steps 50 --warmup 10                      # 1 GPU
+    torchrun --nproc-per-node 8 tools/train_step_bench.py --steps 50 --warmup 10  # 8 GPUs, 16 img/GPU
+    python tools/train_step_bench.py --op ref_cuda      # same model, the reference's own CUDA kernels
+                                                        # (oracle/_ref) behind the reference's own ops/ Python
+
+The step mirrors lib/helpers/trainer_helper.py:116-178: zero_grad, forward, SetCriterion, weighted sum,
+reduce_dict + per-key .item() logging (``--logging faithful``; ``lean`` logs every 30th step only),
+backward, the reference's own AdamW.  No reference file is edited; torch>=2 incompatibilities are
+handled with import shims.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import time
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref", "MonoDETR")
+sys.path.insert(0, ROOT)
+
+
+def install_shims(op: str):
+    if not os.path.isdir(REF):
+        raise SystemExit(f"{REF} missing: run tools/stage_reference.py where /root/reference exists")
+    sys.path.insert(0, REF)
+    # modules the model file imports but never uses on this path
+    for name in ("open3d",):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    import torch.nn.modules.linear as _lin
+    if not hasattr(_lin, "_LinearWithBias"):                       # ops/modules/ms_deform_attn.py:34
+        _lin._LinearWithBias = _lin.NonDynamicallyQuantizableLinear
+    if "torch._overrides" not in sys.modules:                       # ops/modules/ms_deform_attn.py:55
+        import torch.overrides as _ov
+        fake = types.ModuleType("torch._overrides")
+        fake.has_torch_function, fake.handle_torch_function = _ov.has_torch_function, _ov.handle_torch_function
+        sys.modules["torch._overrides"] = fake
+    if op == "ours":
+        import monosowa_b200.ops as b200_ops
+        sys.modules["lib.models.monodetr.ops"] = b200_ops
+        sys.modules["lib.models.monodetr.ops.modules"] = b200_ops.modules
+        sys.modules["lib.models.monodetr.ops.functions"] = b200_ops.functions
+    elif op == "ref_cuda":
+        # the reference's own ops/ Python on top of the reference's own kernels (oracle/_ref)
+        from oracle import msda_oracle as O
+        ext = types.ModuleType("MultiScaleDeformableAttention")
+        ext.ms_deform_attn_forward = lambda v, sh, lsi, loc, aw, step: O.ref_cuda_forward(v, sh, lsi, loc, aw)
+        ext.ms_deform_attn_backward = lambda v, sh, lsi, loc, aw, g, step: O.ref_cuda_backward(v, sh, lsi, loc, aw, g.contiguous())
+        sys.modules["MultiScaleDeformableAttention"] = ext
+    else:
+        raise ValueError(op)
+
+
+def synthetic_batch(batch, device, seed, n_obj=8, max_objs=50):
+    """N(0,1) images (B,3,384,1280), P2 calib, 8 synthetic Car labels/image."""
+    g = torch.Generator().manual_seed(seed)
+    U = lambda lo, hi, *shape: torch.rand(*shape, generator=g) * (hi - lo) + lo
+    images = torch.randn(batch, 3, 384, 1280, generator=g)
+    P2 = torch.tensor([[721.5, 0.0, 609.6, 44.9], [0.0, 721.5, 172.9, 0.2], [0.0, 0.0, 1.0, 0.003]])
+    calibs = P2[None].repeat(batch, 1, 1)
+    t = {
+        "calibs": P2[None, None].repeat(batch, max_objs, 1, 1),
+        "img_size": torch.tensor([[1242.0, 375.0]]).repeat(batch, 1),
+        "labels": torch.zeros(batch, max_objs, dtype=torch.int8),
+        "boxes": torch.zeros(batch, max_objs, 4), "boxes_3d": torch.zeros(batch, max_objs, 6),
+        "depth": torch.zeros(batch, max_objs, 1), "size_3d": torch.zeros(batch, max_objs, 3),
+        "heading_bin": torch.zeros(batch, max_objs, 1, dtype=torch.int64),
+        "heading_res": torch.zeros(batch, max_objs, 1), "mask_2d": torch.zeros(batch, max_objs, dtype=torch.bool),
+    }
+    cx, cy = U(0.1, 0.9, batch, n_obj), U(0.4, 0.8, batch, n_obj)
+    l, r = U(0.02, 0.08, batch, n_obj), U(0.02, 0.08, batch, n_obj)
+    tp, b = U(0.02, 0.1, batch, n_obj), U(0.02, 0.1, batch, n_obj)
+    t["boxes_3d"][:, :n_obj] = torch.stack([cx, cy, l, r, tp, b], -1)
+    t["boxes"][:, :n_obj] = torch.stack([cx + (r - l) / 2, cy + (b - tp) / 2, l + r, tp + b], -1)
+    t["depth"][:, :n_obj, 0] = U(5.0, 60.0, batch, n_obj)
+    t["size_3d"][:, :n_obj] = torch.tensor([1.5, 1.6, 3.9]) * U(0.9, 1.1, batch, n_obj, 3)
+    t["heading_bin"][:, :n_obj, 0] = torch.randint(0, 12, (batch, n_obj), generator=g)
+    t["heading_res"][:, :n_obj, 0] = U(-0.26, 0.26, batch, n_obj)
+    t["labels"][:, :n_obj] = 1
+    t["mask_2d"][:, :n_obj] = True
+    return images.to(device), calibs.to(device), {k: v.to(device) for k, v in t.items()}
+
+
+def prepare_targets(targets, batch_size):                 # trainer_helper.py:180-191
+    keys = ["labels", "boxes", "calibs", "depth", "size_3d", "heading_bin", "heading_res", "boxes_3d"]
+    mask = targets["mask_2d"]
+    return [{k: targets[k][i][mask[i]] for k in keys} for i in range(batch_size)]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--op", default="ours", choices=["ours", "ref_cuda"])
+    ap.add_argument("--logging", default="faithful", choices=["faithful", "lean"])
+    ap.add_argument("--profile-msda", action="store_true", help="kineto pass: MSDA kernels' share of the step")
+    args = ap.parse_args()
+
+    rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 8) // max(world, 1))))
+    torch.set_num_threads(max(1, (os.cpu_count() or 8) // max(world, 1)))
+
+    install_shims(args.op)
+    import yaml
+    from lib.models.monodetr import build as build_monodetr
+    from lib.helpers.optimizer_helper import build_optimizer
+    from utils import misc
+    cfg = yaml.load(open(os.path.join(REF, "configs", "monodetr.yaml")), Loader=yaml.Loader)
+    cfg["model"]["pretrained"] = False                      # no network for torchvision weights
+    torch.manual_seed(cfg.get("random_seed", 444))
+    model, criterion = build_monodetr(cfg["model"])
+    model.to(dev).train()
+    criterion.train()
+    n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    optimizer = build_optimizer(cfg["optimizer"], model)
+    images, calibs, tdict = synthetic_batch(args.batch, dev, seed=1237 + rank)
+    targets = prepare_targets(tdict, args.batch)
+    img_sizes = tdict["img_size"]
+    weight_dict = criterion.weight_dict
+
+    net = model
+    if world > 1:
+        # one dry step without DDP to learn whether every parameter receives a gradient
+        out = model(images, calibs, targets, img_sizes, dn_args=None)
+        ld = criterion(out, targets, None, None)
+        sum(ld[k] * weight_dict[k] for k in ld if k in weight_dict).backward()
+        unused = any(p.requires_grad and p.grad is None for p in model.parameters())
+        optimizer.zero_grad()
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=unused,
+                                                        gradient_as_bucket_view=True)
+
+    def step(i):
+        optimizer.zero_grad()
+        outputs = net(images, calibs, targets, img_sizes, dn_args=None)
+        ld = criterion(outputs, targets, None, None)
+        loss = sum(ld[k] * weight_dict[k] for k in ld.keys() if k in weight_dict)
+        if args.logging == "faithful" or i % 30 == 0:           # trainer_helper.py:150-158
+            red = misc.reduce_dict(ld)
+            _ = sum((red[k] * weight_dict[k]).item() for k in red if k in weight_dict)
+        loss.backward()
+        optimizer.step()
+        return loss
+
+    for i in range(args.warmup):
+        loss = step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t0 = time.perf_counter()
+    ev[0].record()
+    for i in range(args.steps):
+        loss = step(i + 1)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    ms = torch.tensor([statistics.median(per), sum(per) / len(per), wall * 1e3 / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+
+    share = None
+    if args.profile_msda and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for i in range(3):
+                step(i + 1)
+            torch.cuda.synchronize()
+        tot = msda_t = 0.0
+        for e in prof.key_averages():
+            dt = getattr(e, "device_time_total", 0.0) or getattr(e, "cuda_time_total", 0.0)
+            if e.device_type == torch.autograd.DeviceType.CUDA:
+                tot += dt
+                if "msda::" in e.key or "ms_deformable" in e.key or "rec_kernel" in e.key or "vec_kernel" in e.key:
+                    msda_t += dt
+        share = {"gpu_kernel_ms_per_step": tot / 3e3, "msda_kernel_ms_per_step": msda_t / 3e3,
+                 "msda_share_of_gpu_time": msda_t / tot if tot else None}
+    elif args.profile_msda and world > 1:
+        for i in range(3):
+            step(i + 1)                                          # keep the ranks in lock step
+
+    if rank == 0:
+        med, mean, wallms = ms.tolist()
+        print(json.dumps({
+            "metric": "MonoDETR train img/s", "value": args.batch * world / (mean * 1e-3), "unit": "img/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean, "ms_per_step_median": med,
+            "ms_per_step_wall": wallms, "scaling": "weak", "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[3]: unmodified reference MonoDETR (ResNet-50, 3 enc + 3 dec layers) + "
+                                   "SetCriterion + reference AdamW, synthetic KITTI batch", "batch_per_gpu": args.batch,
+                       "global_batch": args.batch * world, "image": [384, 1280], "msda_op": args.op, "logging": args.logging,
+                       "parallelism": f"ddp{world}", "trainable_params": n_params},
+            "loss": float(loss), "msda": share}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
