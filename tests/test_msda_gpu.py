@@ -409,6 +409,64 @@ def test_c_abi_direct_call_and_error_codes(msda, cuda_device):
     assert rc == 0 and O.rel_l2(out2, out) < 2e-6
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
+@pytest.mark.parametrize("shape", [([(5, 7), (3, 4), (1, 1)], 2, 8, 32, 37, 4), ([(4, 3)], 1, 3, 16, 9, 2), ([(6, 5), (2, 2)], 1, 2, 24, 5, 3)])
+def test_guard_bands_no_out_of_bounds_access(msda, cuda_device, dtype, shape):
+    """compute-sanitizer is closed on this GPU pool, so bounds are checked the hard way: every tensor
+    is carved out of a larger buffer whose surroundings are NaN (inputs) or a sentinel (outputs), the
+    locations hammer the borders, and the kernels are called through the raw C ABI.  An out-of-range
+    read poisons the results with NaN (even at weight 0); an out-of-range write breaks a sentinel."""
+    shapes, N, M, D, Lq, P = shape
+    value, sh, lsi, loc, attn, grad_out = _random_case(31, shapes, N, M, D, Lq, P, spread=1.6, shift=-0.3)
+    border = torch.tensor([-1e-4, 0.0, 1e-4, 0.5, 1.0 - 1e-4, 1.0, 1.0 + 1e-4, -0.2, 1.2], dtype=torch.float64)
+    pick = torch.randint(0, len(border), loc.shape, generator=torch.Generator().manual_seed(5))
+    loc = torch.where(torch.rand(loc.shape, generator=torch.Generator().manual_seed(6)) < 0.5, border[pick], loc)
+    dev, ct = cuda_device, (torch.float64 if dtype == torch.float64 else torch.float32)
+    gvt = ct                                                       # grad_value accumulates in fp32 / fp64
+    GUARD = 4096                                                   # elements on each side
+
+    def carve(t, fill):
+        buf = torch.full((t.numel() + 2 * GUARD,), fill, dtype=t.dtype, device=dev)
+        view = buf[GUARD:GUARD + t.numel()].view(t.shape)
+        return buf, view
+
+    bufs = {}
+    ins = dict(value=value.to(dtype), loc=loc.to(ct), attn=attn.to(ct), grad_out=grad_out.to(dtype))
+    views = {}
+    for k, t in ins.items():
+        bufs[k], views[k] = carve(t.to(dev), float("nan"))
+        views[k].copy_(t)
+    outs = dict(out=torch.empty(N, Lq, M * D, dtype=dtype), gv=torch.empty(value.shape, dtype=gvt),
+                gl=torch.empty(loc.shape, dtype=ct), ga=torch.empty(attn.shape, dtype=ct))
+    SENT = 4096.0                                                  # exactly representable in bf16
+    for k, t in outs.items():
+        bufs[k], views[k] = carve(t.to(dev), SENT)
+    lib = msda._lib.lib
+    sfx = {torch.float32: "f32", torch.bfloat16: "bf16", torch.float64: "f64"}[dtype]
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    shd, lsid = sh.to(dev), lsi.to(dev)
+    S, L = int(sh.prod(1).sum()), len(shapes)
+    rc = getattr(lib, "msda_forward_" + sfx)(p(views["value"]), p(shd), p(lsid), p(views["loc"]), p(views["attn"]),
+                                             p(views["out"]), N, S, M, D, L, Lq, P, st)
+    assert rc == 0, msda._lib.last_error()
+    rc = getattr(lib, "msda_backward_" + sfx)(p(views["value"]), p(shd), p(lsid), p(views["loc"]), p(views["attn"]),
+                                              p(views["grad_out"]), p(views["gv"]), p(views["gl"]), p(views["ga"]),
+                                              N, S, M, D, L, Lq, P, st)
+    assert rc == 0, msda._lib.last_error()
+    torch.cuda.synchronize()
+    for k in outs:
+        assert torch.isfinite(views[k].float()).all(), f"{k}: NaN leaked in -> out-of-range read"
+        b = bufs[k].float()
+        assert (b[:GUARD] == SENT).all() and (b[-GUARD:] == SENT).all(), f"{k}: guard band overwritten"
+    args = (ins["value"].double(), sh, lsi, ins["loc"].double(), ins["attn"].double())
+    tol = TOL[dtype]
+    assert O.rel_l2(views["out"], O.forward_c(*args)) <= tol["fwd"]
+    rgv, rgl, rga = O.backward_c(*args, ins["grad_out"].double())
+    assert O.rel_l2(views["gv"], rgv) <= (1e-4 if dtype == torch.bfloat16 else tol["gv"])   # fp32 accumulator here
+    assert O.rel_l2(views["ga"], rga) <= tol["ga"]
+
+
 def test_side_stream_and_cuda_graph(msda, cuda_device):
     from monosowa_b200 import workloads as W
     d = W.make_inputs(W.config(0, batch=1), device=cuda_device)
