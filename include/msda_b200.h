@@ -58,6 +58,7 @@ enum {
     MSDA_ERR_NULL_POINTER = -1, /* a required pointer is NULL (and the tensor is non-empty) */
     MSDA_ERR_BAD_SHAPE = -2,    /* negative size, L > MSDA_MAX_LEVELS, or a size overflow   */
     MSDA_ERR_MISALIGNED = -3,   /* a pointer is not aligned to its element size             */
+    MSDA_ERR_UNSUPPORTED = -4,  /* fused entry points only: no fused kernel for this shape  */
 };
 
 /* ---- fp32: value/loc/attn/out all float ------------------------------------------------ */
@@ -99,6 +100,37 @@ int msda_backward_bf16(const void *value, const int64_t *spatial_shapes,
                        const void *attn_weight, const void *grad_out,
                        void *grad_value_f32, void *grad_loc, void *grad_attn,
                        int N, int S, int M, int D, int L, int Lq, int P, void *stream);
+
+/* ---- fused pre-processing -----------------------------------------
+ * Same op, but the kernels consume the RAW outputs of the module's two Linears and build the
+ * sampling locations and softmax weights in registers -- what the reference module does in PyTorch
+ * at ops/modules/ms_deform_attn.py:145-151 for 2-dim reference points:
+ *     attn = softmax(attn_logits over L*P);   loc = reference_points[l] + sampling_offsets / (W_l, H_l)
+ *   reference_points [N, Lq, L, 2] float (not differentiated here), sampling_offsets [N, Lq, M, L, P, 2]
+ *   float, attn_logits [N, Lq, M, L*P] float; value / out / grad_out float or bf16 as above.
+ *   backward writes grad_value (fp32 accumulator, zero-filled here), grad_offsets, grad_logits.
+ * Supported: D in {16, 32, 64}, L*P <= D, 16-byte aligned pointers; otherwise MSDA_ERR_UNSUPPORTED
+ * is returned and nothing is launched (callers fall back to the unfused entry points). */
+int msda_forward_fused_f32(const void *value, const int64_t *spatial_shapes,
+                           const int64_t *level_start_index, const void *reference_points,
+                           const void *sampling_offsets, const void *attn_logits, void *out,
+                           int N, int S, int M, int D, int L, int Lq, int P, void *stream);
+int msda_forward_fused_bf16(const void *value, const int64_t *spatial_shapes,
+                            const int64_t *level_start_index, const void *reference_points,
+                            const void *sampling_offsets, const void *attn_logits, void *out,
+                            int N, int S, int M, int D, int L, int Lq, int P, void *stream);
+int msda_backward_fused_f32(const void *value, const int64_t *spatial_shapes,
+                            const int64_t *level_start_index, const void *reference_points,
+                            const void *sampling_offsets, const void *attn_logits,
+                            const void *grad_out, void *grad_value, void *grad_offsets,
+                            void *grad_logits, int N, int S, int M, int D, int L, int Lq, int P,
+                            void *stream);
+int msda_backward_fused_bf16(const void *value, const int64_t *spatial_shapes,
+                             const int64_t *level_start_index, const void *reference_points,
+                             const void *sampling_offsets, const void *attn_logits,
+                             const void *grad_out, void *grad_value_f32, void *grad_offsets,
+                             void *grad_logits, int N, int S, int M, int D, int L, int Lq, int P,
+                             void *stream);
 
 /* ---- introspection ---------------------------------------------------------------------- */
 int msda_abi_version(void);            /* == MSDA_ABI_VERSION                                */

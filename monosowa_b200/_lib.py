@@ -14,10 +14,14 @@ LIB_PATH = os.path.join(_PKG, "libmsda_b200.so")
 _vp, _i64p, _int = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int
 _FWD = [_vp, _i64p, _i64p, _vp, _vp, _vp] + [_int] * 7 + [_vp]
 _BWD = [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]
+_FFWD = [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]
+_FBWD = [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]
 
 EXPORTS = {
     "msda_forward_f32": (_int, _FWD), "msda_forward_f64": (_int, _FWD), "msda_forward_bf16": (_int, _FWD),
     "msda_backward_f32": (_int, _BWD), "msda_backward_f64": (_int, _BWD), "msda_backward_bf16": (_int, _BWD),
+    "msda_forward_fused_f32": (_int, _FFWD), "msda_forward_fused_bf16": (_int, _FFWD),
+    "msda_backward_fused_f32": (_int, _FBWD), "msda_backward_fused_bf16": (_int, _FBWD),
     "msda_abi_version": (_int, []),
     "msda_build_info": (ctypes.c_char_p, []),
     "msda_last_error": (ctypes.c_char_p, []),
@@ -28,6 +32,7 @@ EXPORTS = {
     "msda_describe_backward": (ctypes.c_char_p, [_int] * 5),
 }
 ABI_VERSION = 1
+ERR_UNSUPPORTED = -4
 
 
 def _open() -> ctypes.CDLL:

@@ -140,13 +140,17 @@ bwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
 //      H*a*(hx(t10-t00)+lx(t11-t01)))  (ms_deform_im2col_cuda.cuh:119-158) and writes them,
 //      overwriting every element exactly once (zeros for outside samples, cuh:365-367).
 // ------------------------------------------------------------------------------------------------
-template <typename VT, int D, int MINB>
+// FUSED: `loc` = raw sampling offsets, `attn` = raw logits, `ref` = (N,Lq,L,2)
+// reference points; `grad_loc` receives d/d offsets = grad_loc / (W,H) and `grad_attn` receives
+// d/d logits = a * (grad_a - sum_j a_j grad_a_j)  (softmax backward over the L*P samples).
+template <typename VT, int D, int MINB, bool FUSED = false>
 __global__ void __launch_bounds__(256, MINB)
 bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                const float *__restrict__ attn, const VT *__restrict__ grad_out,
                float *__restrict__ grad_value, float *__restrict__ grad_loc,
-               float *__restrict__ grad_attn, const Dims d, const int order)
+               float *__restrict__ grad_attn, const Dims d, const int order,
+               const float *__restrict__ ref = nullptr)
 {
     constexpr int G = D / kChannelsPerLane;
     using RL = RecordLayout<G>;
@@ -174,14 +178,33 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     float g[4];
     Vec4<VT>::load(grad_out + qm * D + gl * kChannelsPerLane, g);
 
-    SampleIn in = fetch_sample(w.valid && gl < LP, loc, attn, qm * LP + gl);
+    float aw[kMaxBatches];                          // FUSED: softmax weights of this lane's samples ...
+    float pa[kMaxBatches], pg[kMaxBatches];         // ... and, per processed batch, (a, d out / d a)
+    if constexpr (FUSED) {
+        group_softmax<G>(attn, qm * LP, LP, gl, w.valid, aw);
+#pragma unroll
+        for (int b = 0; b < kMaxBatches; ++b) pa[b] = pg[b] = 0.f;
+    }
+    auto fetch = [&](int sidx) -> SampleIn {
+        const bool has = w.valid && sidx < LP;
+        if constexpr (FUSED) {
+            const int l = has ? sidx / d.P : 0;
+            const SampleIn r = fetch_sample_fused(has, loc, ref, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l, aw[0]);
+            aw[0] = aw[1]; aw[1] = aw[2]; aw[2] = aw[3];
+            return r;
+        } else {
+            return fetch_sample(has, loc, attn, qm * LP + sidx);
+        }
+    };
+    SampleIn in = fetch(gl);
     for (int b0 = 0; b0 < LP; b0 += G) {
         const int sidx = b0 + gl;
         const bool has = w.valid && sidx < LP;
         const SampleGeom gm = build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, has && d.S > 0, in, s_lv,
                                            sidx / d.P, xs);
+        const float a_cur = in.a;
         __syncwarp();
-        in = fetch_sample(w.valid && sidx + G < LP, loc, attn, qm * LP + sidx + G);       // next batch, in flight
+        in = fetch(sidx + G);                                                              // next batch, in flight
 
         float t[4 * G];
 #pragma unroll
@@ -225,8 +248,33 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 gy = gm.Hf * gm.a * (gm.hx * (t10 - t00) + gm.lx * (t11 - t01));
             }
             const long si = qm * LP + sidx;
-            *reinterpret_cast<float2 *>(grad_loc + 2 * si) = make_float2(gx, gy);
-            grad_attn[si] = ga;
+            if constexpr (FUSED) {
+                // d loc / d offset = 1 / (W, H); outside samples have gx = gy = 0 (Wf = Hf = 0 there)
+                const float ox = gm.live ? __fdiv_rn(gx, gm.Wf) : 0.f, oy = gm.live ? __fdiv_rn(gy, gm.Hf) : 0.f;
+                *reinterpret_cast<float2 *>(grad_loc + 2 * si) = make_float2(ox, oy);
+                pa[0] = pa[1]; pa[1] = pa[2]; pa[2] = pa[3]; pa[3] = a_cur;       // queue of (a, grad_a), newest last
+                pg[0] = pg[1]; pg[1] = pg[2]; pg[2] = pg[3]; pg[3] = ga;
+            } else {
+                *reinterpret_cast<float2 *>(grad_loc + 2 * si) = make_float2(gx, gy);
+                grad_attn[si] = ga;
+            }
+        } else if constexpr (FUSED) {
+            pa[0] = pa[1]; pa[1] = pa[2]; pa[2] = pa[3]; pa[3] = 0.f;
+            pg[0] = pg[1]; pg[1] = pg[2]; pg[2] = pg[3]; pg[3] = 0.f;
+        }
+    }
+    if constexpr (FUSED) {
+        // softmax backward: grad_logit_i = a_i * (g_i - sum_j a_j g_j); the queue holds the last
+        // nb = ceil(LP / G) batches at positions kMaxBatches - nb ... kMaxBatches - 1
+        float dot = 0.f;
+#pragma unroll
+        for (int b = 0; b < kMaxBatches; ++b) dot += pa[b] * pg[b];
+        dot = group_allreduce_sum<G>(dot);
+        const int nb = (LP + G - 1) / G;
+#pragma unroll
+        for (int b = 0; b < kMaxBatches; ++b) {
+            const int sidx = (b - (kMaxBatches - nb)) * G + gl;
+            if (b >= kMaxBatches - nb && w.valid && sidx < LP) grad_attn[qm * LP + sidx] = pa[b] * (pg[b] - dot);
         }
     }
 }
@@ -412,6 +460,57 @@ int run_generic(const void *value, const int64_t *shapes, const int64_t *lsi, co
 }
 
 }  // namespace
+
+namespace {
+template <typename VT, int D>
+int run_rec_fused(const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref, const void *offsets,
+                  const void *logits, const void *grad_out, void *gv, void *goff, void *glogit, const Dims &d,
+                  cudaStream_t st)
+{
+    constexpr int G = D / kChannelsPerLane;
+    const long grid = grid_for(d, 1, 32 / G, 256);
+#define MSDA_BWD_FUSED(MINB)                                                                                         \
+    bwd_rec_kernel<VT, D, MINB, true><<<(unsigned)grid, 256, 0, st>>>(                                               \
+        (const VT *)value, shapes, lsi, (const float *)offsets, (const float *)logits, (const VT *)grad_out, (float *)gv, \
+        (float *)goff, (float *)glogit, d, 1, (const float *)ref)
+    if (D > 32) MSDA_BWD_FUSED(1);
+    else if (tuning().bwd_pipe == 2) MSDA_BWD_FUSED(2);
+    else MSDA_BWD_FUSED(3);
+#undef MSDA_BWD_FUSED
+    count_launch();
+    return (int)cudaGetLastError();
+}
+}  // namespace
+
+int launch_backward_fused(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref,
+                          const void *offsets, const void *logits, const void *grad_out, void *gv, void *goff,
+                          void *glogit, const Dims &d, cudaStream_t st)
+{
+    if ((long)d.S * d.M * d.D >= (1L << 31) || dt == DType::F64) return kUnsupported;
+    if (!(d.D == 16 || d.D == 32 || d.D == 64) || d.L * d.P > kMaxBatches * (d.D / kChannelsPerLane)) return kUnsupported;
+    const size_t gv_bytes = 4 * (size_t)d.N * d.S * d.M * d.D;
+    if (gv_bytes) {
+        cudaError_t e = cudaMemsetAsync(gv, 0, gv_bytes, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if ((long)d.N * d.Lq * d.M == 0) return 0;
+#define FUSED_ARGS value, shapes, lsi, ref, offsets, logits, grad_out, gv, goff, glogit, d, st
+    if (dt == DType::F32) {
+        switch (d.D) {
+        case 16: return run_rec_fused<float, 16>(FUSED_ARGS);
+        case 32: return run_rec_fused<float, 32>(FUSED_ARGS);
+        case 64: return run_rec_fused<float, 64>(FUSED_ARGS);
+        }
+    } else {
+        switch (d.D) {
+        case 16: return run_rec_fused<__nv_bfloat16, 16>(FUSED_ARGS);
+        case 32: return run_rec_fused<__nv_bfloat16, 32>(FUSED_ARGS);
+        case 64: return run_rec_fused<__nv_bfloat16, 64>(FUSED_ARGS);
+        }
+    }
+#undef FUSED_ARGS
+    return kUnsupported;
+}
 
 const char *backward_kernel_name(DType dt, int D, int L, int P, bool vec_ok)
 {

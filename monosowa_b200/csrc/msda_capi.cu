@@ -106,6 +106,32 @@ static int backward_impl(const char *fn, DType dt, const void *value, const int6
         launch_backward(dt, value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, c.d, c.vec_ok, (cudaStream_t)stream), fn);
 }
 
+static int fused_impl(const char *fn, DType dt, bool backward, const void *value, const int64_t *shapes,
+                      const int64_t *lsi, const void *ref, const void *offsets, const void *logits, const void *grad_out,
+                      void *o0, void *o1, void *o2, int N, int S, int M, int D, int L, int Lq, int P, void *stream)
+{
+    Checked c;
+    if (int rc = check_common(fn, dt, value, shapes, lsi, offsets, logits, N, S, M, D, L, Lq, P, &c)) return rc;
+    const bool has_q = (long long)N * Lq * M > 0;
+    if (has_q && L > 0 && !ref) return fail(MSDA_ERR_NULL_POINTER, "%s: reference_points is NULL", fn);
+    if (!backward && !c.empty_out && !o0) return fail(MSDA_ERR_NULL_POINTER, "%s: out is NULL", fn);
+    if (backward && ((!c.empty_out && !grad_out) || ((long long)N * S * M * D > 0 && !o0) ||
+                     ((long long)N * Lq * M * L * P > 0 && (!o1 || !o2))))
+        return fail(MSDA_ERR_NULL_POINTER, "%s: a gradient pointer is NULL", fn);
+    const bool al = c.vec_ok && aligned(ref, 8) && aligned(o0, 16) && aligned(o1, 8) && aligned(o2, 4) && aligned(grad_out, 8);
+    if (!al) return fail(MSDA_ERR_UNSUPPORTED, "%s: pointers are not 16-byte aligned", fn);
+    int rc;
+    if (!backward) {
+        if (c.empty_out) return cuda_result(0, fn);
+        rc = launch_forward_fused(dt, value, shapes, lsi, ref, offsets, logits, o0, c.d, (cudaStream_t)stream);
+    } else {
+        rc = launch_backward_fused(dt, value, shapes, lsi, ref, offsets, logits, grad_out, o0, o1, o2, c.d, (cudaStream_t)stream);
+    }
+    if (rc == kUnsupported)
+        return fail(MSDA_ERR_UNSUPPORTED, "%s: no fused kernel for D=%d L*P=%d (use the unfused entry points)", fn, D, L * P);
+    return cuda_result(rc, fn);
+}
+
 }  // namespace msda
 
 using namespace msda;
@@ -131,6 +157,37 @@ int msda_forward_bf16(FWD_ARGS) { return forward_impl("msda_forward_bf16", DType
 int msda_backward_f32(BWD_ARGS) { return backward_impl("msda_backward_f32", DType::F32, BWD_PASS); }
 int msda_backward_f64(BWD_ARGS) { return backward_impl("msda_backward_f64", DType::F64, BWD_PASS); }
 int msda_backward_bf16(BWD_ARGS) { return backward_impl("msda_backward_bf16", DType::BF16, BWD_PASS); }
+
+#define FUSED_FWD_ARGS                                                                               \
+    const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,              \
+        const void *reference_points, const void *sampling_offsets, const void *attn_logits, void *out, \
+        int N, int S, int M, int D, int L, int Lq, int P, void *stream
+#define FUSED_BWD_ARGS                                                                               \
+    const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,              \
+        const void *reference_points, const void *sampling_offsets, const void *attn_logits,         \
+        const void *grad_out, void *grad_value, void *grad_offsets, void *grad_logits, int N, int S, \
+        int M, int D, int L, int Lq, int P, void *stream
+
+int msda_forward_fused_f32(FUSED_FWD_ARGS)
+{
+    return fused_impl("msda_forward_fused_f32", DType::F32, false, value, spatial_shapes, level_start_index, reference_points,
+                      sampling_offsets, attn_logits, nullptr, out, nullptr, nullptr, N, S, M, D, L, Lq, P, stream);
+}
+int msda_forward_fused_bf16(FUSED_FWD_ARGS)
+{
+    return fused_impl("msda_forward_fused_bf16", DType::BF16, false, value, spatial_shapes, level_start_index, reference_points,
+                      sampling_offsets, attn_logits, nullptr, out, nullptr, nullptr, N, S, M, D, L, Lq, P, stream);
+}
+int msda_backward_fused_f32(FUSED_BWD_ARGS)
+{
+    return fused_impl("msda_backward_fused_f32", DType::F32, true, value, spatial_shapes, level_start_index, reference_points,
+                      sampling_offsets, attn_logits, grad_out, grad_value, grad_offsets, grad_logits, N, S, M, D, L, Lq, P, stream);
+}
+int msda_backward_fused_bf16(FUSED_BWD_ARGS)
+{
+    return fused_impl("msda_backward_fused_bf16", DType::BF16, true, value, spatial_shapes, level_start_index, reference_points,
+                      sampling_offsets, attn_logits, grad_out, grad_value, grad_offsets, grad_logits, N, S, M, D, L, Lq, P, stream);
+}
 
 int msda_abi_version(void) { return MSDA_ABI_VERSION; }
 

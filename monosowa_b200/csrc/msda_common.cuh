@@ -249,6 +249,13 @@ int launch_forward(DType dt, const void *value, const int64_t *shapes, const int
 int launch_backward(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi,
                     const void *loc, const void *attn, const void *grad_out, void *grad_value,
                     void *grad_loc, void *grad_attn, const Dims &d, bool vec_ok, cudaStream_t st);
+// fused pre-processing entry points; return kUnsupported when no fused kernel fits
+constexpr int kUnsupported = -1000;
+int launch_forward_fused(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref,
+                         const void *offsets, const void *logits, void *out, const Dims &d, cudaStream_t st);
+int launch_backward_fused(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref,
+                          const void *offsets, const void *logits, const void *grad_out, void *grad_value,
+                          void *grad_offsets, void *grad_logits, const Dims &d, cudaStream_t st);
 const char *forward_kernel_name(DType dt, int D, int L, int P, bool vec_ok);
 const char *backward_kernel_name(DType dt, int D, int L, int P, bool vec_ok);
 

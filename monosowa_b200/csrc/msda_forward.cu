@@ -104,11 +104,14 @@ fwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
 // record kernel (second generation, see msda_records.cuh): geometry computed once per sample by
 // one lane, shared through shared memory; any L and P; D in {16, 32, 64}; fp32 or bf16 values.
 // ------------------------------------------------------------------------------------------------
-template <typename VT, int D, int MINB, bool COMPACT>
+// FUSED: `loc` holds the raw sampling offsets, `attn` the raw attention logits and
+// `ref` the (N,Lq,L,2) reference points; locations and softmax weights are formed in registers.
+template <typename VT, int D, int MINB, bool COMPACT, bool FUSED = false>
 __global__ void __launch_bounds__(256, MINB)
 fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ lsi, const float *__restrict__ loc,
-               const float *__restrict__ attn, VT *__restrict__ out, const Dims d, const int order)
+               const float *__restrict__ attn, VT *__restrict__ out, const Dims d, const int order,
+               const float *__restrict__ ref = nullptr)
 {
     constexpr int G = D / kChannelsPerLane;
     using RL = RecordLayout<G>;
@@ -133,7 +136,20 @@ fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
 
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (d.S > 0) {
-        SampleIn in = fetch_sample(w.valid && gl < LP, loc, attn, qm * LP + gl);
+        float aw[kMaxBatches];                      // FUSED: softmax weights of this lane's samples
+        if constexpr (FUSED) group_softmax<G>(attn, qm * LP, LP, gl, w.valid, aw);
+        auto fetch = [&](int sidx) -> SampleIn {
+            const bool has = w.valid && sidx < LP;
+            if constexpr (FUSED) {
+                const int l = has ? sidx / d.P : 0;
+                const SampleIn r = fetch_sample_fused(has, loc, ref, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l, aw[0]);
+                aw[0] = aw[1]; aw[1] = aw[2]; aw[2] = aw[3];          // aw[0] = weight of the next batch
+                return r;
+            } else {
+                return fetch_sample(has, loc, attn, qm * LP + sidx);
+            }
+        };
+        SampleIn in = fetch(gl);
         for (int b0 = 0; b0 < LP; b0 += G) {
             const int sidx = b0 + gl;
             if constexpr (COMPACT) {
@@ -149,7 +165,7 @@ fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                     *reinterpret_cast<float4 *>(grp + RL::WEIGHTS + slot * 4) = *reinterpret_cast<const float4 *>(tmp + 4);
                 }
                 __syncwarp();
-                in = fetch_sample(w.valid && sidx + G < LP, loc, attn, qm * LP + sidx + G);
+                in = fetch(sidx + G);
                 for (int s = 0; s < cnt; ++s) {
                     const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
                     const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
@@ -167,7 +183,7 @@ fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
             }
             build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, w.valid && sidx < LP, in, s_lv, sidx / d.P, xs);
             __syncwarp();
-            in = fetch_sample(w.valid && sidx + G < LP, loc, attn, qm * LP + sidx + G);   // next batch, in flight
+            in = fetch(sidx + G);                                     // next batch, in flight
 #pragma unroll
             for (int s = 0; s < G; ++s) {
                 const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
@@ -354,6 +370,47 @@ bool use_rec(const Dims &d, bool vec_ok)
 }
 
 }  // namespace
+
+namespace {
+template <typename VT, int D>
+int run_rec_fused(const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref, const void *offsets,
+                  const void *logits, void *out, const Dims &d, cudaStream_t st)
+{
+    constexpr int G = D / kChannelsPerLane;
+    if (d.L * d.P > kMaxBatches * G) return kUnsupported;
+    const long grid = grid_for(d, 1, 32 / G, 256);
+    if (sizeof(VT) == 4)
+        fwd_rec_kernel<VT, D, 5, true, true><<<(unsigned)grid, 256, 0, st>>>(
+            (const VT *)value, shapes, lsi, (const float *)offsets, (const float *)logits, (VT *)out, d, 1, (const float *)ref);
+    else
+        fwd_rec_kernel<VT, D, 6, false, true><<<(unsigned)grid, 256, 0, st>>>(
+            (const VT *)value, shapes, lsi, (const float *)offsets, (const float *)logits, (VT *)out, d, 1, (const float *)ref);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+}  // namespace
+
+int launch_forward_fused(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref,
+                         const void *offsets, const void *logits, void *out, const Dims &d, cudaStream_t st)
+{
+    if ((long)d.S * d.M * d.D >= (1L << 31) || dt == DType::F64) return kUnsupported;
+#define FUSED_ARGS value, shapes, lsi, ref, offsets, logits, out, d, st
+    if (dt == DType::F32) {
+        switch (d.D) {
+        case 16: return run_rec_fused<float, 16>(FUSED_ARGS);
+        case 32: return run_rec_fused<float, 32>(FUSED_ARGS);
+        case 64: return run_rec_fused<float, 64>(FUSED_ARGS);
+        }
+    } else {
+        switch (d.D) {
+        case 16: return run_rec_fused<__nv_bfloat16, 16>(FUSED_ARGS);
+        case 32: return run_rec_fused<__nv_bfloat16, 32>(FUSED_ARGS);
+        case 64: return run_rec_fused<__nv_bfloat16, 64>(FUSED_ARGS);
+        }
+    }
+#undef FUSED_ARGS
+    return kUnsupported;
+}
 
 const char *forward_kernel_name(DType dt, int D, int L, int P, bool vec_ok)
 {

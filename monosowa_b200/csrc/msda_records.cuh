@@ -100,6 +100,74 @@ __device__ __forceinline__ SampleIn fetch_sample(bool has, const float *__restri
     return in;
 }
 
+// ---- fused pre-processing -------------------------------------------------
+// In fused mode the kernels consume the RAW outputs of the module's two Linears
+// (reference ops/modules/ms_deform_attn.py:145-151):
+//   loc  = reference_point[l] + sampling_offset / (W_l, H_l)          (2-dim reference points)
+//   attn = softmax over the L*P logits of a (query, head)
+// so the (N,Lq,M,L,P,2) locations and (N,Lq,M,L,P) weights never exist in HBM.  A lane owns the
+// samples {gl, gl+G, gl+2G, ...} of its (query, head): at most kMaxBatches of them.
+constexpr int kMaxBatches = 4;
+
+template <int G>
+__device__ __forceinline__ float group_allreduce_max(float v)
+{
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, off));
+    return v;
+}
+
+template <int G>
+__device__ __forceinline__ float group_allreduce_sum(float v)
+{
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(kFullMask, v, off);
+    return v;
+}
+
+// softmax over the L*P logits of this lane group; a[b] is the weight of sample b*G + gl
+template <int G>
+__device__ __forceinline__ void group_softmax(const float *__restrict__ logits, long base, int LP, int gl, bool valid,
+                                              float (&a)[kMaxBatches])
+{
+    float x[kMaxBatches];
+    float m = -INFINITY;
+#pragma unroll
+    for (int b = 0; b < kMaxBatches; ++b) {
+        const bool has = valid && (b * G + gl < LP);
+        x[b] = has ? __ldg(logits + base + b * G + gl) : -INFINITY;
+        m = fmaxf(m, x[b]);
+    }
+    m = group_allreduce_max<G>(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int b = 0; b < kMaxBatches; ++b) {
+        a[b] = (x[b] == -INFINITY) ? 0.f : expf(x[b] - m);
+        sum += a[b];
+    }
+    sum = group_allreduce_sum<G>(sum);
+#pragma unroll
+    for (int b = 0; b < kMaxBatches; ++b) a[b] = (sum > 0.f) ? a[b] / sum : 0.f;
+}
+
+// fused fetch: offset + reference point -> normalised location (same operation order as torch:
+// ref + off / size, IEEE division); the attention weight comes from group_softmax
+__device__ __forceinline__ SampleIn fetch_sample_fused(bool has, const float *__restrict__ offsets,
+                                                       const float *__restrict__ ref, long sample_index,
+                                                       long ref_index, const LevelInfo *s_lv, int l, float a)
+{
+    SampleIn in{0.f, 0.f, 0.f};
+    if (has) {
+        const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + sample_index);
+        const float2 r = __ldg(reinterpret_cast<const float2 *>(ref) + ref_index);
+        const LevelInfo li = s_lv[l];
+        in.x = r.x + __fdiv_rn(o.x, (float)li.W);
+        in.y = r.y + __fdiv_rn(o.y, (float)li.H);
+        in.a = a;
+    }
+    return in;
+}
+
 // Build the record of one sample and write it to `rec_off` / `rec_w` (16-byte aligned).  The
 // weights stored are w_ij * a (what both forward and grad_value need).
 __device__ __forceinline__ SampleGeom build_record(uint32_t *rec_off, uint32_t *rec_w, bool has, const SampleIn in,

@@ -30,6 +30,11 @@ _LIBDEF.define("forward(Tensor value, Tensor spatial_shapes, Tensor level_start_
 _LIBDEF.define("backward(Tensor value, Tensor spatial_shapes, Tensor level_start_index, "
                "Tensor sampling_locations, Tensor attention_weights, Tensor grad_output, "
                "int im2col_step) -> (Tensor, Tensor, Tensor)")
+_LIBDEF.define("forward_fused(Tensor value, Tensor spatial_shapes, Tensor level_start_index, "
+               "Tensor reference_points, Tensor sampling_offsets, Tensor attention_logits) -> Tensor")
+_LIBDEF.define("backward_fused(Tensor value, Tensor spatial_shapes, Tensor level_start_index, "
+               "Tensor reference_points, Tensor sampling_offsets, Tensor attention_logits, "
+               "Tensor grad_output) -> (Tensor, Tensor, Tensor)")
 
 
 def _check(value, spatial_shapes, level_start_index, loc, attn, im2col_step, grad_output=None):
@@ -146,9 +151,82 @@ def _backward_cuda(value, spatial_shapes, level_start_index, sampling_locations,
     return grad_value, grad_loc, grad_attn
 
 
+# ------------------------------------------------------------------------------------------------
+# fused pre-processing: softmax over L*P and ref + offset / (W, H) inside the kernels
+# ------------------------------------------------------------------------------------------------
+def fused_supported(value, reference_points, n_levels, n_points):
+    """True when the fused kernels can take this call (else use the unfused op)."""
+    d = value.shape[-1]
+    return (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16) and d in (16, 32, 64)
+            and n_levels * n_points <= d and reference_points.shape[-1] == 2)
+
+
+def _fused_views(value, reference_points, sampling_offsets, attention_logits):
+    n, s, m, d = value.shape
+    _, lq, _, nl, p, _ = sampling_offsets.shape
+    if tuple(reference_points.shape) != (n, lq, nl, 2) or attention_logits.numel() != n * lq * m * nl * p \
+            or sampling_offsets.shape[0] != n or sampling_offsets.shape[2] != m:
+        raise RuntimeError(f"inconsistent shapes for the fused op: value {tuple(value.shape)}, "
+                           f"ref {tuple(reference_points.shape)}, offsets {tuple(sampling_offsets.shape)}, "
+                           f"logits {tuple(attention_logits.shape)}")
+    f32 = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous()
+    return (n, s, m, d, nl, lq, p), f32(reference_points), f32(sampling_offsets), f32(attention_logits)
+
+
+def _forward_fused_cuda(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits):
+    for name, t in (("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index)):
+        if not t.is_cuda:
+            raise NotImplementedError(f"{name} must be a CUDA tensor: MSDA is not implemented on the CPU")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+    dims, ref, off, logit = _fused_views(value, reference_points, sampling_offsets, attention_logits)
+    n, s, m, d, nl, lq, p = dims
+    out = torch.empty((n, lq, m * d), dtype=value.dtype, device=value.device)
+    fn = getattr(_lib.lib, "msda_forward_fused_" + _SUFFIX[value.dtype])
+    with _on_device(value.device) as stream:
+        rc = fn(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(ref), _ptr(off), _ptr(logit), _ptr(out),
+                n, s, m, d, nl, lq, p, stream)
+    if rc:
+        _raise(rc, "msda::forward_fused")
+    return out
+
+
+def _backward_fused_cuda(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                         attention_logits, grad_output):
+    dims, ref, off, logit = _fused_views(value, reference_points, sampling_offsets, attention_logits)
+    n, s, m, d, nl, lq, p = dims
+    grad_output = grad_output.contiguous()
+    if grad_output.dtype != value.dtype:
+        grad_output = grad_output.to(value.dtype)
+    grad_value = torch.empty(value.shape, dtype=torch.float32, device=value.device)
+    grad_off = torch.empty(off.shape, dtype=torch.float32, device=value.device)
+    grad_logit = torch.empty(logit.shape, dtype=torch.float32, device=value.device)
+    fn = getattr(_lib.lib, "msda_backward_fused_" + _SUFFIX[value.dtype])
+    with _on_device(value.device) as stream:
+        rc = fn(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(ref), _ptr(off), _ptr(logit),
+                _ptr(grad_output), _ptr(grad_value), _ptr(grad_off), _ptr(grad_logit), n, s, m, d, nl, lq, p, stream)
+    if rc:
+        _raise(rc, "msda::backward_fused")
+    return (grad_value.to(value.dtype), grad_off.to(sampling_offsets.dtype), grad_logit.to(attention_logits.dtype))
+
+
 _LIBIMPL = torch.library.Library("msda", "IMPL")
 _LIBIMPL.impl("forward", _forward_cuda, "CUDA")
 _LIBIMPL.impl("backward", _backward_cuda, "CUDA")
+_LIBIMPL.impl("forward_fused", _forward_fused_cuda, "CUDA")
+_LIBIMPL.impl("backward_fused", _backward_fused_cuda, "CUDA")
+
+
+@torch.library.register_fake("msda::forward_fused")
+def _forward_fused_fake(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits):
+    n, _, m, d = value.shape
+    return value.new_empty((n, sampling_offsets.shape[1], m * d))
+
+
+@torch.library.register_fake("msda::backward_fused")
+def _backward_fused_fake(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                         attention_logits, grad_output):
+    return (torch.empty_like(value), torch.empty_like(sampling_offsets), torch.empty_like(attention_logits))
 
 
 @torch.library.register_fake("msda::forward")
@@ -199,6 +277,29 @@ class MSDeformAttnFunction(Function):
             value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
             grad_output, ctx.im2col_step)
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+
+class MSDeformAttnFusedFunction(Function):
+    """MSDA with the module's pre-processing folded into the kernels:
+    ``apply(value, spatial_shapes, level_start_index, reference_points (N,Lq,L,2),
+    sampling_offsets (N,Lq,M,L,P,2), attention_logits (N,Lq,M,L*P))`` equals
+    ``MSDeformAttnFunction.apply(value, shapes, lsi, ref[:, :, None, :, None, :] + offsets / (W,H),
+    softmax(logits, -1).view(N,Lq,M,L,P), im2col_step)``.  ``reference_points`` is not
+    differentiated (gradient None): the module only takes this path when it does not need one."""
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits):
+        out = torch.ops.msda.forward_fused(value, spatial_shapes, level_start_index, reference_points,
+                                           sampling_offsets, attention_logits)
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                              attention_logits)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        gv, goff, glogit = torch.ops.msda.backward_fused(*ctx.saved_tensors, grad_output)
+        return gv, None, None, None, goff, glogit
 
 
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):

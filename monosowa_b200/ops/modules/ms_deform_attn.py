@@ -21,7 +21,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..functions import MSDeformAttnFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported
 
 
 def _is_power_of_2(n):
@@ -53,6 +53,9 @@ class MSDeformAttn(nn.Module):
             warnings.warn("You'd better set d_model in MSDeformAttn to make the dimension of each attention head "
                           "a power of 2 which is more efficient in our CUDA implementation.")
         self.im2col_step = 64                      # reference :87; kept for API parity (validated, not needed)
+        # fold softmax + "ref + offset / (W,H)" into the kernels when the call allows it
+        # (2-dim reference points that need no gradient -- the encoder); set False for the literal path
+        self.fuse_preprocessing = True
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
         self.conditional = conditional
         self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
@@ -94,6 +97,11 @@ class MSDeformAttn(nn.Module):
         value = value.view(n, len_in, self.n_heads, value.shape[-1] // self.n_heads)
         offsets = self.sampling_offsets(query).view(n, len_q, self.n_heads, self.n_levels, self.n_points, 2)
         weights = self.attention_weights(query).view(n, len_q, self.n_heads, self.n_levels * self.n_points)
+        if (self.fuse_preprocessing and not reference_points.requires_grad
+                and fused_supported(value, reference_points, self.n_levels, self.n_points)):
+            output = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                                     reference_points, offsets, weights)
+            return self.output_proj(output)
         if value.dtype == torch.bfloat16:
             # bf16 carries 8 mantissa bits: not enough for sub-pixel coordinates at W=160.  Keep the
             # location / weight arithmetic in fp32 (the bf16 kernels take fp32 loc & weights).

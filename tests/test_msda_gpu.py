@@ -511,6 +511,90 @@ def test_registered_op_autograd_and_fake(msda, cuda_device):
 
 
 # --------------------------------------------------------------------------------------------
+# 6b. fused pre-processing: softmax + ref + offset/(W,H) inside the kernels
+# --------------------------------------------------------------------------------------------
+FUSED_CASES = [
+    ([(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 131, 4),
+    ([(9, 7), (5, 4), (3, 3)], 2, 4, 32, 19, 3),              # L*P = 9: ragged second batch
+    ([(9, 7), (5, 4)], 3, 3, 16, 17, 2),                      # 4-lane groups, one batch
+    ([(9, 7), (5, 4), (3, 3), (2, 2)], 1, 2, 64, 9, 4),       # 16-lane groups
+    ([(9, 7), (5, 4), (3, 3), (2, 2)], 1, 2, 16, 9, 4),       # L*P = 16 = 4 batches of 4 lanes
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: f"M{c[2]}D{c[3]}Lq{c[4]}P{c[5]}L{len(c[0])}")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_preprocessing_matches_unfused_and_oracle(msda, cuda_device, case, dtype):
+    from monosowa_b200.ops.functions import MSDeformAttnFusedFunction, fused_supported
+    shapes, N, M, D, Lq, P = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(77 + D + Lq)
+    sh, lsi = _levels(shapes)
+    S, L = int(sh.prod(1).sum()), len(shapes)
+    value = torch.randn(N, S, M, D, generator=g).to(dev, dtype)
+    ref = (torch.rand(N, Lq, L, 2, generator=g) * 1.2 - 0.1).to(dev)
+    offs = (torch.randn(N, Lq, M, L, P, 2, generator=g) * 3.0).to(dev)
+    logits = (torch.randn(N, Lq, M, L * P, generator=g) * 2.0).to(dev)
+    grad_out = torch.randn(N, Lq, M * D, generator=g).to(dev, dtype)
+    shd, lsid = sh.to(dev), lsi.to(dev)
+    assert fused_supported(value, ref, L, P)
+
+    def unfused(v, o, lg):
+        wh = torch.stack([shd[:, 1], shd[:, 0]], -1)
+        loc = ref[:, :, None, :, None, :] + o / wh[None, None, None, :, None, :]
+        aw = torch.softmax(lg, -1).view(N, Lq, M, L, P)
+        return msda.MSDeformAttnFunction.apply(v, shd, lsid, loc.contiguous(), aw.contiguous(), 64), loc, aw
+
+    res = []
+    for fused in (True, False):
+        v = value.clone().requires_grad_(True); o = offs.clone().requires_grad_(True); lg = logits.clone().requires_grad_(True)
+        if fused:
+            out = MSDeformAttnFusedFunction.apply(v, shd, lsid, ref, o, lg)
+        else:
+            out, loc, aw = unfused(v, o, lg)
+        out.backward(grad_out)
+        res.append((out.detach(), v.grad, o.grad, lg.grad))
+    (fo, fgv, fgo, fgl), (uo, ugv, ugo, ugl) = res
+    t_out, t_gv = (2e-6, 1e-5) if dtype == torch.float32 else (4e-3, 1e-2)
+    assert O.rel_l2(fo, uo) < t_out
+    assert O.rel_l2(fgv, ugv) < t_gv
+    assert O.rel_l2(fgl, ugl) < 1e-5
+    # offsets: same floor() decisions (identical fp32 location arithmetic), so no masking needed
+    assert O.rel_l2(fgo, ugo) < 1e-5
+    # and against the fp64 oracle on the locations / weights torch produced
+    ref_out = O.forward_c(value.cpu().double(), sh, lsi, loc.detach().cpu().double(), aw.detach().cpu().double())
+    assert O.rel_l2(fo, ref_out) < (1e-5 if dtype == torch.float32 else 4e-3)
+
+
+def test_module_takes_the_fused_path_only_when_allowed(msda, cuda_device, monkeypatch):
+    from monosowa_b200.ops.modules import ms_deform_attn as modfile
+    calls = []
+    real_f, real_u = modfile.MSDeformAttnFusedFunction.apply, modfile.MSDeformAttnFunction.apply
+
+    class F_:
+        apply = staticmethod(lambda *a: (calls.append("fused"), real_f(*a))[1])
+
+    class U_:
+        apply = staticmethod(lambda *a: (calls.append("unfused"), real_u(*a))[1])
+
+    monkeypatch.setattr(modfile, "MSDeformAttnFusedFunction", F_)
+    monkeypatch.setattr(modfile, "MSDeformAttnFunction", U_)
+    dev = cuda_device
+    sh, lsi = _levels([(6, 8), (3, 4)])
+    mod = msda.MSDeformAttn(64, 2, 4, 2).to(dev)
+    q, src = torch.randn(2, 7, 64, device=dev), torch.randn(2, 60, 64, device=dev)
+    ref2 = torch.rand(2, 7, 2, 2, device=dev)
+    out_f = mod(q, ref2, src, sh.to(dev), lsi.to(dev))
+    mod.fuse_preprocessing = False
+    out_u = mod(q, ref2, src, sh.to(dev), lsi.to(dev))
+    mod.fuse_preprocessing = True
+    mod(q, ref2.clone().requires_grad_(True), src, sh.to(dev), lsi.to(dev))        # needs d/d ref -> unfused
+    mod(q, torch.rand(2, 7, 2, 6, device=dev) * 0.3, src, sh.to(dev), lsi.to(dev))  # 6-dim refs -> unfused
+    assert calls == ["fused", "unfused", "unfused", "unfused"]
+    assert O.rel_l2(out_f, out_u) < 2e-6
+
+
+# --------------------------------------------------------------------------------------------
 # 7. the MSDeformAttn module against goldens produced by the reference module
 # --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["ref2", "ref6"])
