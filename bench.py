@@ -209,17 +209,23 @@ def run_ours(args, wl):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                     # started before warm-up: nvidia-smi needs ~0.1 s to come up
+    # Warm-up keeps the previous step's outputs alive while the next step allocates, exactly like the
+    # timed loop below, so the caching allocator has reached its steady state (no cudaMalloc inside
+    # the timed region); the 0.3 s pre-warm lets clocks settle before the W warm-up steps.
     t_pre = time.perf_counter()
-    while time.perf_counter() - t_pre < 0.3:        # clock / allocator / L2 settle before the W warm-up steps
-        step_device()
-        torch.cuda.synchronize()
+    keep = None
+    while time.perf_counter() - t_pre < 0.3:
+        keep = step_device()
+    torch.cuda.synchronize()
     for _ in range(args.warmup):
-        step_device()
+        keep = step_device()
+    del keep
     barrier()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     n0 = msda._lib.launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
+    out = grads = None
     for i in range(args.steps):
         ev[i][0].record()
         out = fwd_op(*a5, 64)
@@ -233,6 +239,9 @@ def run_ours(args, wl):
     ms_step = t_start.elapsed_time(t_end) / args.steps
     fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
     bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
+    if os.environ.get("MSDA_BENCH_TRACE") and rank == 0:       # per-step trace for drift / throttling diagnosis
+        with open(os.environ["MSDA_BENCH_TRACE"], "w") as f:
+            json.dump({"fwd_ms": [e[0].elapsed_time(e[1]) for e in ev], "bwd_ms": [e[1].elapsed_time(e[2]) for e in ev]}, f)
 
     def reduce_fn(t, op):
         tt = t.to(dev)

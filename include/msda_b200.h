@@ -139,13 +139,15 @@ const char *msda_last_error(void);     /* thread-local; "" when the last call su
 long long msda_launch_count(void);     /* kernels this library has launched so far (memsets excluded) */
 
 /* Kernel-selection knobs, for benchmarking A/B runs only (process-wide, not thread-safe
- * against concurrent launches).  key: "fwd_variant", "bwd_variant", "block_threads".
- * value -1 restores the default heuristic.  Returns MSDA_OK or MSDA_ERR_BAD_SHAPE (unknown key). */
+ * against concurrent launches).  Keys: "fwd_variant" / "bwd_variant" (10, 11 = record kernel with
+ * work order 0 / 1, 99 = generic kernels), "fwd_pipe" / "bwd_pipe" (register-cap / loop flavour of
+ * the record kernels, see the launch code).  value -1 restores the measured default.
+ * Returns MSDA_OK or MSDA_ERR_BAD_SHAPE (unknown key). */
 int msda_set_tuning(const char *key, int value);
 int msda_get_tuning(const char *key);
 
-/* Name of the kernel the current heuristics pick for this problem, e.g. "fwd_vec_f32_d32_p4"
- * or "fwd_generic_f64" (static storage; for logs, tests and bench.py). */
+/* Name of the kernel family the current heuristics pick for this problem: "fwd_rec_f32",
+ * "bwd_rec_bf16", "fwd_generic_f64", ... (static storage; for logs, tests and bench.py). */
 const char *msda_describe_forward(int dtype_bits, int is_bf16, int D, int L, int P);
 const char *msda_describe_backward(int dtype_bits, int is_bf16, int D, int L, int P);
 

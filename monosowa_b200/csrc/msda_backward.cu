@@ -2,136 +2,23 @@
 //
 // Replaces the reference's seven col2im kernels and their dispatcher (reference
 // MonoDETR/lib/models/monodetr/ops/src/cuda/ms_deform_im2col_cuda.cuh:301-920, 956-1327;
-// gradient formulas :87-159).  Machine mapping (see also msda_forward.cu):
-//   * a lane owns a 128-bit channel vector; D/VEC lanes form the lane group of one (query, head);
-//   * grad_value: one REDG.E.ADD.F32x4 (red.global.add.v4.f32) per lane per corner instead of
-//     four scalar atomicAdds -- the reference issues 4 scalar atomics per channel per sample;
+// gradient formulas :87-159).  Machine mapping (see also msda_forward.cu, msda_records.cuh):
+//   * a lane owns 4 channels; D/4 lanes form the lane group of one (query, head); the bilinear
+//     geometry of a sample is computed once by one lane and shared through a shared-memory record;
+//   * grad_value: one REDG.E.ADD.F32x4 (red.global.add.v4.f32) per lane per corner -- 8 lanes emit one
+//     full 128-byte reduction line -- instead of the reference's 4 scalar atomics per channel per sample;
 //   * grad_sampling_loc / grad_attn_weight: per-lane partial dot products are combined with a
-//     butterfly reduce-scatter over the lane group (warp shuffles only) and written once, fully
-//     overwriting the outputs -- no shared memory, no block barriers, no zero-fill needed
-//     (the reference: smem staging, 2 __syncthreads and a serial D-way sum per sample point);
-//   * level geometry is staged in shared memory once per CTA.
+//     butterfly reduce-scatter over the lane group (warp shuffles only) and every element is written
+//     exactly once -- no block barriers, no zero-fill (the reference: smem staging, 2 __syncthreads
+//     and a serial D-way sum per sample point).
+// The bound is the SM->L2 reduction port.
 #include "msda_common.cuh"
 #include "msda_records.cuh"
 
 namespace msda {
 
-template <typename VT, int D, int P>
-__global__ void __launch_bounds__(512)
-bwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
-               const int64_t *__restrict__ lsi, const float *__restrict__ loc,
-               const float *__restrict__ attn, const VT *__restrict__ grad_out,
-               float *__restrict__ grad_value, float *__restrict__ grad_loc,
-               float *__restrict__ grad_attn, const Dims d, const int order)
-{
-    constexpr int VEC = Vec<VT>::N;
-    constexpr int G = D / VEC;
-    constexpr int QPW = 32 / G;
-    static_assert(D % VEC == 0 && G >= 1 && G <= 32 && (32 % G) == 0, "unsupported D");
-
-    __shared__ LevelInfo s_lv[MSDA_MAX_LEVELS];
-    stage_levels(s_lv, shapes, lsi, d.L);
-
-    const int lane = threadIdx.x & 31;
-    const int gl = lane % G;
-    WorkItem w = decode_work<QPW>(d, order, lane / G);
-    // warps are all-or-nothing past the end of the problem; inside a live warp, lane groups
-    // beyond Lq keep running (they take part in the shuffles) with every sample masked off.
-    if (__ballot_sync(kFullMask, w.valid) == 0) return;
-    if (!w.valid) { w.n = 0; w.q = 0; w.m = 0; }
-
-    const long qm = ((long)w.n * d.Lq + w.q) * d.M + w.m;
-    const long img = ((long)w.n * d.S * d.M + w.m) * D + gl * VEC;
-    const VT *vimg = value + img;
-    float *gvimg = grad_value + img;
-    const float *lp = loc + qm * (long)(d.L * P * 2);
-    const float *ap = attn + qm * (long)(d.L * P);
-    float *glp = grad_loc + qm * (long)(d.L * P * 2);
-    float *gap = grad_attn + qm * (long)(d.L * P);
-    const int xs = d.M * D;
-
-    float g[VEC];
-    Vec<VT>::load(grad_out + qm * D + gl * VEC, g);
-
-    for (int l = 0; l < d.L; ++l) {
-        const LevelInfo li = s_lv[l];
-        const long lvl_off = (long)li.start * xs;
-        const VT *vl = vimg + lvl_off;
-        float *gvl = gvimg + lvl_off;
-        const int ys = li.W * xs;
-
-        float lxy[2 * P], aw[P];
-#pragma unroll
-        for (int i = 0; i < P / 2; ++i) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(lp) + i);
-            lxy[4 * i] = t.x; lxy[4 * i + 1] = t.y; lxy[4 * i + 2] = t.z; lxy[4 * i + 3] = t.w;
-        }
-#pragma unroll
-        for (int i = 0; i < P / 4; ++i) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(ap) + i);
-            aw[4 * i] = t.x; aw[4 * i + 1] = t.y; aw[4 * i + 2] = t.z; aw[4 * i + 3] = t.w;
-        }
-        lp += 2 * P;
-        ap += P;
-
-        float pxy[2 * P], pa[P];
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            pxy[2 * p] = 0.f; pxy[2 * p + 1] = 0.f; pa[p] = 0.f;
-            const Tap<float> t = make_tap(lxy[2 * p], lxy[2 * p + 1], li.H, li.W);
-            if (!t.inside || !w.valid) continue;
-            const bool y0ok = t.y0 >= 0, y1ok = t.y0 + 1 <= li.H - 1;
-            const bool x0ok = t.x0 >= 0, x1ok = t.x0 + 1 <= li.W - 1;
-            const int o00 = t.y0 * ys + t.x0 * xs;
-            float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) v00[c] = v01[c] = v10[c] = v11[c] = 0.f;
-            if (y0ok && x0ok) Vec<VT>::load(vl + o00, v00);
-            if (y0ok && x1ok) Vec<VT>::load(vl + o00 + xs, v01);
-            if (y1ok && x0ok) Vec<VT>::load(vl + o00 + ys, v10);
-            if (y1ok && x1ok) Vec<VT>::load(vl + o00 + ys + xs, v11);
-            const float hy = 1.f - t.ly, hx = 1.f - t.lx;
-            const float w00 = hy * hx, w01 = hy * t.lx, w10 = t.ly * hx, w11 = t.ly * t.lx;
-            const float a = aw[p];
-            float sx = 0.f, sy = 0.f, sa = 0.f;
-            float tg[VEC];
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) {
-                tg[c] = g[c] * a;                                          // cuh:111
-                const float dgx = hy * (v01[c] - v00[c]) + t.ly * (v11[c] - v10[c]);   // cuh:119-149
-                const float dgy = hx * (v10[c] - v00[c]) + t.lx * (v11[c] - v01[c]);
-                sx += dgx * tg[c];
-                sy += dgy * tg[c];
-                sa += g[c] * (w00 * v00[c] + w01 * v01[c] + w10 * v10[c] + w11 * v11[c]);  // cuh:155-156
-            }
-            pxy[2 * p] = (float)li.W * sx;                                 // cuh:157
-            pxy[2 * p + 1] = (float)li.H * sy;                             // cuh:158
-            pa[p] = sa;
-#pragma unroll
-            for (int c = 0; c < VEC; c += 4) {
-                if (y0ok && x0ok)
-                    red_add_f32x4(gvl + o00 + c, w00 * tg[c], w00 * tg[c + 1], w00 * tg[c + 2], w00 * tg[c + 3]);
-                if (y0ok && x1ok)
-                    red_add_f32x4(gvl + o00 + xs + c, w01 * tg[c], w01 * tg[c + 1], w01 * tg[c + 2], w01 * tg[c + 3]);
-                if (y1ok && x0ok)
-                    red_add_f32x4(gvl + o00 + ys + c, w10 * tg[c], w10 * tg[c + 1], w10 * tg[c + 2], w10 * tg[c + 3]);
-                if (y1ok && x1ok)
-                    red_add_f32x4(gvl + o00 + ys + xs + c, w11 * tg[c], w11 * tg[c + 1], w11 * tg[c + 2], w11 * tg[c + 3]);
-            }
-        }
-        group_reduce_scatter<G, 2 * P>(pxy, gl);
-        group_reduce_scatter<G, P>(pa, gl);
-        if (w.valid) {
-            group_store<G, 2 * P>(glp, pxy, gl);
-            group_store<G, P>(gap, pa, gl);
-        }
-        glp += 2 * P;
-        gap += P;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// record kernel (second generation, see msda_records.cuh).  Per batch of G samples:
+// record kernel (see msda_records.cuh).  Per batch of G samples:
 //   1. lane s of a lane group builds the geometry record of sample s (kept privately as well);
 //   2. every lane walks the G records: 4 corner loads of its 4 channels, 4 partial dot products
 //      t_ij = sum_c g_c * v_ij,c  and one REDG.E.ADD.F32x4 per contributing corner ((w_ij*a) * g);
@@ -206,37 +93,59 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
         __syncwarp();
         in = fetch(sidx + G);                                                              // next batch, in flight
 
-        float t[4 * G];
+        // The G samples of the batch are consumed in two halves so that only 2*G partial dot products
+        // are live at a time (t[4*G] costs 32 registers at G = 8 and caps the kernel at 3 CTAs/SM).
+        // After the reduce-scatter of a half, lane j holds corner pair (j & 1) of the half's sample j / 2;
+        // the owner of sample s then pulls its four totals from lanes 2*(s % (G/2)) and +1 of half s / (G/2).
+        constexpr int GH = G / 2;
+        float th[2][2];
 #pragma unroll
-        for (int s = 0; s < G; ++s) {
-            t[4 * s] = t[4 * s + 1] = t[4 * s + 2] = t[4 * s + 3] = 0.f;
-            const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
-            const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
-            if (d.S > 0) {
-                float v00[4], v01[4], v10[4], v11[4];
-                Vec4<VT>::load(vimg + off.x, v00);
-                Vec4<VT>::load(vimg + off.y, v01);
-                Vec4<VT>::load(vimg + off.z, v10);
-                Vec4<VT>::load(vimg + off.w, v11);
+        for (int h = 0; h < 2; ++h) {
+            float t[4 * GH];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    t[4 * s] += g[c] * v00[c];
-                    t[4 * s + 1] += g[c] * v01[c];
-                    t[4 * s + 2] += g[c] * v10[c];
-                    t[4 * s + 3] += g[c] * v11[c];
+            for (int u = 0; u < GH; ++u) {
+                const int s = h * GH + u;
+                t[4 * u] = t[4 * u + 1] = t[4 * u + 2] = t[4 * u + 3] = 0.f;
+                const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
+                const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
+                if (d.S > 0) {
+                    float v00[4], v01[4], v10[4], v11[4];
+                    Vec4<VT>::load(vimg + off.x, v00);
+                    Vec4<VT>::load(vimg + off.y, v01);
+                    Vec4<VT>::load(vimg + off.z, v10);
+                    Vec4<VT>::load(vimg + off.w, v11);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        t[4 * u] += g[c] * v00[c];
+                        t[4 * u + 1] += g[c] * v01[c];
+                        t[4 * u + 2] += g[c] * v10[c];
+                        t[4 * u + 3] += g[c] * v11[c];
+                    }
                 }
+                // a zero weight contributes nothing to grad_value (corner outside the map, sample outside
+                // the window, a == 0, or an exactly integral coordinate): skip the reduction -- the
+                // SM->L2 reduction port is the scarce resource of this kernel
+                if (wa.x != 0.f) red_add_f32x4(gvimg + off.x, wa.x * g[0], wa.x * g[1], wa.x * g[2], wa.x * g[3]);
+                if (wa.y != 0.f) red_add_f32x4(gvimg + off.y, wa.y * g[0], wa.y * g[1], wa.y * g[2], wa.y * g[3]);
+                if (wa.z != 0.f) red_add_f32x4(gvimg + off.z, wa.z * g[0], wa.z * g[1], wa.z * g[2], wa.z * g[3]);
+                if (wa.w != 0.f) red_add_f32x4(gvimg + off.w, wa.w * g[0], wa.w * g[1], wa.w * g[2], wa.w * g[3]);
             }
-            // a zero weight contributes nothing to grad_value (corner outside the map, sample outside
-            // the window, a == 0, or an exactly integral coordinate): skip the reduction -- the
-            // SM->L2 reduction port is the scarce resource of this kernel
-            if (wa.x != 0.f) red_add_f32x4(gvimg + off.x, wa.x * g[0], wa.x * g[1], wa.x * g[2], wa.x * g[3]);
-            if (wa.y != 0.f) red_add_f32x4(gvimg + off.y, wa.y * g[0], wa.y * g[1], wa.y * g[2], wa.y * g[3]);
-            if (wa.z != 0.f) red_add_f32x4(gvimg + off.z, wa.z * g[0], wa.z * g[1], wa.z * g[2], wa.z * g[3]);
-            if (wa.w != 0.f) red_add_f32x4(gvimg + off.w, wa.w * g[0], wa.w * g[1], wa.w * g[2], wa.w * g[3]);
+            group_reduce_scatter<G, 4 * GH>(t, gl);
+            th[h][0] = t[0];
+            th[h][1] = t[1];
         }
         __syncwarp();
 
-        group_reduce_scatter<G, 4 * G>(t, gl);          // lane s now holds t00,t01,t10,t11 of sample s
+        float t[4];
+        {
+            const int src = (lane & ~(G - 1)) | (2 * (gl % GH));
+            const bool second = gl >= GH;
+            const float a0 = __shfl_sync(kFullMask, th[0][0], src), a1 = __shfl_sync(kFullMask, th[0][1], src);
+            const float a2 = __shfl_sync(kFullMask, th[0][0], src + 1), a3 = __shfl_sync(kFullMask, th[0][1], src + 1);
+            const float b0 = __shfl_sync(kFullMask, th[1][0], src), b1 = __shfl_sync(kFullMask, th[1][1], src);
+            const float b2 = __shfl_sync(kFullMask, th[1][0], src + 1), b3 = __shfl_sync(kFullMask, th[1][1], src + 1);
+            t[0] = second ? b0 : a0; t[1] = second ? b1 : a1; t[2] = second ? b2 : a2; t[3] = second ? b3 : a3;
+        }
         if (has) {
             float gx = 0.f, gy = 0.f, ga = 0.f;
             if (gm.live) {
@@ -359,35 +268,11 @@ bwd_generic_kernel(const VT *__restrict__ value, const int64_t *__restrict__ sha
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-template <typename VT>
-constexpr bool vec_supported(int D, int P)
-{
-    if (P != 4) return false;
-    if (sizeof(VT) == 4) return D == 16 || D == 32 || D == 64;
-    return D == 32 || D == 64;
-}
-
-// Kernel choice (bwd_variant): -1 = measured default, 0/1 = vector kernel with work order 0/1,
-// 10/11 = record kernel with order 0/1, 99 = generic.
-// Default, measured on B200 at configs[1] (profiles/r01_v2_sweep.jsonl): the backward is bound by
-// the SM->L2 reduction port, not by instruction issue, so for fp32 the older vector kernel (64
-// registers, 4 CTAs/SM) still edges out the record kernel (80 registers, 3 CTAs/SM): 1.56 vs
-// 1.61 ms.  For bf16 the record kernel wins clearly (1.56 vs 2.77 ms) because its 8-lane groups
-// emit full 128-byte reduction lines.
-template <typename VT>
-bool use_vec(const Dims &d, bool vec_ok)
-{
-    const int v = tuning().bwd_variant;
-    const bool pick = (v == 0 || v == 1) || (v < 0 && sizeof(VT) == 4);
-    return vec_ok && pick && vec_supported<VT>(d.D, d.P) && (long)d.S * d.M * d.D < (1L << 31);
-}
-
-template <typename VT>
+// bwd_variant: -1 default (record kernel, work order 1); 10/11 record kernel with order 0/1; 99 generic.
 bool use_rec(const Dims &d, bool vec_ok)
 {
-    const int v = tuning().bwd_variant;
-    const bool pick = (v == 10 || v == 11) || (v < 0 && !use_vec<VT>(d, vec_ok));
-    return vec_ok && pick && (d.D == 16 || d.D == 32 || d.D == 64) && (long)d.S * d.M * d.D < (1L << 31);
+    return vec_ok && tuning().bwd_variant != 99 && (d.D == 16 || d.D == 32 || d.D == 64) &&
+           (long)d.S * d.M * d.D < (1L << 31);
 }
 
 template <typename VT, int D>
@@ -426,22 +311,6 @@ int dispatch_rec(const void *value, const int64_t *shapes, const int64_t *lsi, c
     case 64: return run_rec<VT, 64>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st);
     }
     return (int)cudaErrorInvalidValue;
-}
-
-template <typename VT, int D, int P>
-int run_vec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
-            const void *attn, const void *grad_out, void *gv, void *gl, void *ga, const Dims &d,
-            cudaStream_t st)
-{
-    constexpr int QPW = 32 / (D / Vec<VT>::N);
-    const int threads = tuning().block_threads > 0 ? tuning().block_threads : 256;
-    const int order = tuning().bwd_variant == 0 ? 0 : 1;
-    const long grid = grid_for(d, order, QPW, threads);
-    bwd_vec_kernel<VT, D, P><<<(unsigned)grid, threads, 0, st>>>(
-        (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,
-        (float *)gv, (float *)gl, (float *)ga, d, order);
-    count_launch();
-    return (int)cudaGetLastError();
 }
 
 template <typename VT, typename CT>
@@ -518,11 +387,8 @@ const char *backward_kernel_name(DType dt, int D, int L, int P, bool vec_ok)
     Dims d{1, 1, 1, D, 1, 1, P};
     switch (dt) {
     case DType::F64: return "bwd_generic_f64";
-    case DType::F32:
-        return use_rec<float>(d, vec_ok) ? "bwd_rec_f32" : (use_vec<float>(d, vec_ok) ? "bwd_vec_f32" : "bwd_generic_f32");
-    case DType::BF16:
-        return use_rec<__nv_bfloat16>(d, vec_ok) ? "bwd_rec_bf16"
-                                                 : (use_vec<__nv_bfloat16>(d, vec_ok) ? "bwd_vec_bf16" : "bwd_generic_bf16");
+    case DType::F32: return use_rec(d, vec_ok) ? "bwd_rec_f32" : "bwd_generic_f32";
+    case DType::BF16: return use_rec(d, vec_ok) ? "bwd_rec_bf16" : "bwd_generic_bf16";
     }
     return "?";
 }
@@ -540,24 +406,9 @@ int launch_backward(DType dt, const void *value, const int64_t *shapes, const in
     if ((long)d.N * d.Lq * d.M == 0) return 0;
 #define ARGS value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st
     if (dt == DType::F64) return run_generic<double, double>(ARGS);
-    if (dt == DType::F32 && use_rec<float>(d, vec_ok)) return dispatch_rec<float>(ARGS);
-    if (dt == DType::BF16 && use_rec<__nv_bfloat16>(d, vec_ok)) return dispatch_rec<__nv_bfloat16>(ARGS);
-    if (dt == DType::F32) {
-        if (use_vec<float>(d, vec_ok)) {
-            switch (d.D) {
-            case 16: return run_vec<float, 16, 4>(ARGS);
-            case 32: return run_vec<float, 32, 4>(ARGS);
-            case 64: return run_vec<float, 64, 4>(ARGS);
-            }
-        }
-        return run_generic<float, float>(ARGS);
-    }
-    if (use_vec<__nv_bfloat16>(d, vec_ok)) {
-        switch (d.D) {
-        case 32: return run_vec<__nv_bfloat16, 32, 4>(ARGS);
-        case 64: return run_vec<__nv_bfloat16, 64, 4>(ARGS);
-        }
-    }
+    if (dt == DType::F32 && use_rec(d, vec_ok)) return dispatch_rec<float>(ARGS);
+    if (dt == DType::BF16 && use_rec(d, vec_ok)) return dispatch_rec<__nv_bfloat16>(ARGS);
+    if (dt == DType::F32) return run_generic<float, float>(ARGS);
     return run_generic<__nv_bfloat16, float>(ARGS);
 #undef ARGS
 }

@@ -205,7 +205,6 @@ static int *tuning_slot(const char *key)
     if (!key) return nullptr;
     if (!strcmp(key, "fwd_variant")) return &tuning().fwd_variant;
     if (!strcmp(key, "bwd_variant")) return &tuning().bwd_variant;
-    if (!strcmp(key, "block_threads")) return &tuning().block_threads;
     if (!strcmp(key, "fwd_pipe")) return &tuning().fwd_pipe;
     if (!strcmp(key, "bwd_pipe")) return &tuning().bwd_pipe;
     return nullptr;
@@ -215,8 +214,6 @@ int msda_set_tuning(const char *key, int value)
 {
     int *slot = tuning_slot(key);
     if (!slot) return fail(MSDA_ERR_BAD_SHAPE, "msda_set_tuning: unknown key '%s'", key ? key : "(null)");
-    if (!strcmp(key, "block_threads") && value > 0 && (value % 32 != 0 || value > 512))
-        return fail(MSDA_ERR_BAD_SHAPE, "msda_set_tuning: block_threads must be a multiple of 32, <= 512");
     *slot = value;
     return 0;
 }

@@ -80,49 +80,6 @@ __device__ __forceinline__ Tap<double> make_tap(double loc_x, double loc_y, int 
     return t;
 }
 
-// ---- 128-bit channel vectors ---------------------------------------------------------------
-template <typename VT>
-struct Vec;
-
-template <>
-struct Vec<float> {
-    static constexpr int N = 4;
-    static __device__ __forceinline__ void load(const float *p, float (&f)[4])
-    {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
-        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-    }
-    static __device__ __forceinline__ void store(float *p, const float (&f)[4])
-    {
-        *reinterpret_cast<float4 *>(p) = make_float4(f[0], f[1], f[2], f[3]);
-    }
-};
-
-template <>
-struct Vec<__nv_bfloat16> {
-    static constexpr int N = 8;
-    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&f)[8])
-    {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
-        const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {          // bf16 -> fp32 is a 16-bit shift
-            f[2 * i] = __uint_as_float(w[i] << 16);
-            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-        }
-    }
-    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&f)[8])
-    {
-        unsigned w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-            w[i] = *reinterpret_cast<const unsigned *>(&h);
-        }
-        *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-};
-
 // REDG.E.ADD.F32x4: one 16-byte reduction per lane instead of four scalar atomics.
 __device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float c, float d)
 {
@@ -165,20 +122,6 @@ __device__ __forceinline__ void group_reduce_scatter(float (&v)[NV], int gl)
 {
     static_assert((G & (G - 1)) == 0 && (NV & (NV - 1)) == 0, "power-of-two sizes only");
     ReduceScatter<G / 2, NV>::run(v, gl);
-}
-
-// store the result of group_reduce_scatter as a contiguous run of NV floats at dst
-template <int G, int NV>
-__device__ __forceinline__ void group_store(float *dst, const float (&v)[NV], int gl)
-{
-    if constexpr (NV >= G) {
-        constexpr int CNT = NV / G;
-#pragma unroll
-        for (int i = 0; i < CNT; ++i) dst[gl * CNT + i] = v[i];
-    } else {
-        constexpr int REP = G / NV;
-        if ((gl % REP) == 0) dst[gl / REP] = v[0];
-    }
 }
 
 // ---- work decomposition ----------------------------------------------------------------------
@@ -232,7 +175,6 @@ inline long grid_for(const Dims &d, int order, int qpw, int threads)
 struct Tuning {
     int fwd_variant = -1;
     int bwd_variant = -1;
-    int block_threads = -1;
     int fwd_pipe = -1;
     int bwd_pipe = -1;
 };

@@ -4,104 +4,21 @@
 // MonoDETR/lib/models/monodetr/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299) and its
 // launcher (:923-954).  Same arithmetic per sample (see msda_common.cuh), different machine
 // mapping:
-//   * one lane owns a 128-bit channel vector (4 fp32 / 8 bf16 channels), so a sample corner is
-//     one LDG.E.128 per lane and D/VEC lanes (a "lane group") cover one (query, head);
-//   * a warp owns 32/G consecutive queries of one head: neighbouring queries gather
-//     neighbouring pixels, so their corner lines coincide in L1 (and within one instruction on
-//     the coarse levels);
-//   * sampling locations / weights of a level are fetched with 128-bit loads once per lane,
-//     level geometry comes from shared memory, all P points of a level are in flight together.
-// The op is a gather: no tensor cores, the bound is L1/L2 gather bandwidth.
+//   * one lane owns 4 channels (one LDG.E.128 per corner in fp32, LDG.E.64 in bf16) and D/4 lanes
+//     (a "lane group") cover one (query, head); a warp owns 32/G consecutive queries of one head:
+//     neighbouring queries gather neighbouring pixels, so their corner lines coincide in L1;
+//   * the bilinear geometry of a sample is computed ONCE, by one lane of the group, and shared
+//     through a 32-byte shared-memory record (msda_records.cuh) -- the first-generation kernel
+//     recomputed it in all 8 lanes and was instruction-issue bound (profiles/r01_v1_*);
+//   * samples outside the sampling window are compacted away before the gather loop.
+// The op is a gather: no tensor cores; the bound is L1 data-pipe wavefronts.
 #include "msda_common.cuh"
 #include "msda_records.cuh"
 
 namespace msda {
 
 // ------------------------------------------------------------------------------------------------
-// vector kernel: VT in {float, bf16}, D*sizeof(VT) a multiple of 16 with G = D/VEC lanes | 32
-// ------------------------------------------------------------------------------------------------
-template <typename VT, int D, int P>
-__global__ void __launch_bounds__(512)
-fwd_vec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
-               const int64_t *__restrict__ lsi, const float *__restrict__ loc,
-               const float *__restrict__ attn, VT *__restrict__ out, const Dims d, const int order)
-{
-    constexpr int VEC = Vec<VT>::N;
-    constexpr int G = D / VEC;
-    constexpr int QPW = 32 / G;
-    static_assert(D % VEC == 0 && G >= 1 && G <= 32 && (32 % G) == 0, "unsupported D");
-
-    __shared__ LevelInfo s_lv[MSDA_MAX_LEVELS];
-    stage_levels(s_lv, shapes, lsi, d.L);
-
-    const int lane = threadIdx.x & 31;
-    const int gl = lane % G;
-    const WorkItem w = decode_work<QPW>(d, order, lane / G);
-    if (!w.valid) return;
-
-    const long qm = ((long)w.n * d.Lq + w.q) * d.M + w.m;
-    const VT *vimg = value + ((long)w.n * d.S * d.M + w.m) * D + gl * VEC;
-    const float *lp = loc + qm * (long)(d.L * P * 2);
-    const float *ap = attn + qm * (long)(d.L * P);
-    const int xs = d.M * D;                       // element stride between x neighbours
-
-    float acc[VEC];
-#pragma unroll
-    for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
-
-    for (int l = 0; l < d.L; ++l) {
-        const LevelInfo li = s_lv[l];
-        const VT *vl = vimg + (long)li.start * xs;
-        const int ys = li.W * xs;
-
-        float lxy[2 * P], aw[P];
-        if constexpr ((P % 4) == 0) {
-#pragma unroll
-            for (int i = 0; i < P / 2; ++i) {
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(lp) + i);
-                lxy[4 * i] = t.x; lxy[4 * i + 1] = t.y; lxy[4 * i + 2] = t.z; lxy[4 * i + 3] = t.w;
-            }
-#pragma unroll
-            for (int i = 0; i < P / 4; ++i) {
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(ap) + i);
-                aw[4 * i] = t.x; aw[4 * i + 1] = t.y; aw[4 * i + 2] = t.z; aw[4 * i + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 2 * P; ++i) lxy[i] = __ldg(lp + i);
-#pragma unroll
-            for (int i = 0; i < P; ++i) aw[i] = __ldg(ap + i);
-        }
-        lp += 2 * P;
-        ap += P;
-
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const Tap<float> t = make_tap(lxy[2 * p], lxy[2 * p + 1], li.H, li.W);
-            if (!t.inside) continue;
-            const bool y0ok = t.y0 >= 0, y1ok = t.y0 + 1 <= li.H - 1;
-            const bool x0ok = t.x0 >= 0, x1ok = t.x0 + 1 <= li.W - 1;
-            const VT *c00 = vl + (t.y0 * ys + t.x0 * xs);
-            float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) v00[c] = v01[c] = v10[c] = v11[c] = 0.f;
-            if (y0ok && x0ok) Vec<VT>::load(c00, v00);
-            if (y0ok && x1ok) Vec<VT>::load(c00 + xs, v01);
-            if (y1ok && x0ok) Vec<VT>::load(c00 + ys, v10);
-            if (y1ok && x1ok) Vec<VT>::load(c00 + ys + xs, v11);
-            const float hy = 1.f - t.ly, hx = 1.f - t.lx;
-            const float w00 = hy * hx, w01 = hy * t.lx, w10 = t.ly * hx, w11 = t.ly * t.lx;
-            const float a = aw[p];
-#pragma unroll
-            for (int c = 0; c < VEC; ++c)
-                acc[c] += (w00 * v00[c] + w01 * v01[c] + w10 * v10[c] + w11 * v11[c]) * a;
-        }
-    }
-    Vec<VT>::store(out + qm * D + gl * VEC, acc);
-}
-
-// ------------------------------------------------------------------------------------------------
-// record kernel (second generation, see msda_records.cuh): geometry computed once per sample by
+// record kernel (see msda_records.cuh): geometry computed once per sample by
 // one lane, shared through shared memory; any L and P; D in {16, 32, 64}; fp32 or bf16 values.
 // ------------------------------------------------------------------------------------------------
 // FUSED: `loc` holds the raw sampling offsets, `attn` the raw attention logits and
@@ -269,32 +186,6 @@ fwd_generic_kernel(const VT *__restrict__ value, const int64_t *__restrict__ sha
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-struct FwdChoice {
-    const char *name;
-    int kind;  // 0 generic, 1 vec
-};
-
-template <typename VT>
-constexpr bool vec_supported(int D, int P)
-{
-    if (P != 4) return false;
-    if (sizeof(VT) == 4) return D == 16 || D == 32 || D == 64;
-    return D == 32 || D == 64;
-}
-
-template <typename VT, int D, int P>
-int run_vec(const VT *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
-            const float *attn, VT *out, const Dims &d, cudaStream_t st)
-{
-    constexpr int QPW = 32 / (D / Vec<VT>::N);
-    const int threads = tuning().block_threads > 0 ? tuning().block_threads : 256;
-    const int order = tuning().fwd_variant == 0 ? 0 : 1;
-    const long grid = grid_for(d, order, QPW, threads);
-    fwd_vec_kernel<VT, D, P><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order);
-    count_launch();
-    return (int)cudaGetLastError();
-}
-
 template <typename VT, int D>
 int run_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
             const float *attn, VT *out, const Dims &d, int order, cudaStream_t st)
@@ -339,10 +230,9 @@ int dispatch_rec(const void *value, const int64_t *shapes, const int64_t *lsi, c
     return (int)cudaErrorInvalidValue;
 }
 
-// variant: -1 default (records, order 1); 0/1 first-generation vector kernel with order 0/1;
-// 10/11 record kernel with order 0/1; 99 generic.
+// fwd_variant: -1 default (record kernel, work order 1); 10/11 record kernel with order 0/1; 99 generic.
 inline bool rec_supported(const Dims &d) { return d.D == 16 || d.D == 32 || d.D == 64; }
-inline bool want_rec(int variant) { return variant < 0 || variant == 10 || variant == 11; }
+inline bool want_rec(int variant) { return variant != 99; }
 
 template <typename VT, typename CT>
 int run_generic(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
@@ -355,13 +245,6 @@ int run_generic(const void *value, const int64_t *shapes, const int64_t *lsi, co
         (const VT *)value, shapes, lsi, (const CT *)loc, (const CT *)attn, (VT *)out, d);
     count_launch();
     return (int)cudaGetLastError();
-}
-
-template <typename VT>
-bool use_vec(const Dims &d, bool vec_ok)
-{
-    const int v = tuning().fwd_variant;
-    return vec_ok && (v == 0 || v == 1) && vec_supported<VT>(d.D, d.P) && (long)d.S * d.M * d.D < (1L << 31);
 }
 
 bool use_rec(const Dims &d, bool vec_ok)
@@ -418,10 +301,8 @@ const char *forward_kernel_name(DType dt, int D, int L, int P, bool vec_ok)
     Dims d{1, 1, 1, D, 1, 1, P};
     switch (dt) {
     case DType::F64: return "fwd_generic_f64";
-    case DType::F32:
-        return use_rec(d, vec_ok) ? "fwd_rec_f32" : (use_vec<float>(d, vec_ok) ? "fwd_vec_f32" : "fwd_generic_f32");
-    case DType::BF16:
-        return use_rec(d, vec_ok) ? "fwd_rec_bf16" : (use_vec<__nv_bfloat16>(d, vec_ok) ? "fwd_vec_bf16" : "fwd_generic_bf16");
+    case DType::F32: return use_rec(d, vec_ok) ? "fwd_rec_f32" : "fwd_generic_f32";
+    case DType::BF16: return use_rec(d, vec_ok) ? "fwd_rec_bf16" : "fwd_generic_bf16";
     }
     return "?";
 }
@@ -435,27 +316,7 @@ int launch_forward(DType dt, const void *value, const int64_t *shapes, const int
     if (dt == DType::F32 && use_rec(d, vec_ok)) return dispatch_rec<float>(value, shapes, lsi, loc, attn, out, d, rec_order, st);
     if (dt == DType::BF16 && use_rec(d, vec_ok))
         return dispatch_rec<__nv_bfloat16>(value, shapes, lsi, loc, attn, out, d, rec_order, st);
-    if (dt == DType::F32) {
-        if (use_vec<float>(d, vec_ok)) {
-            const float *v = (const float *)value, *lo = (const float *)loc, *at = (const float *)attn;
-            float *o = (float *)out;
-            switch (d.D) {
-            case 16: return run_vec<float, 16, 4>(v, shapes, lsi, lo, at, o, d, st);
-            case 32: return run_vec<float, 32, 4>(v, shapes, lsi, lo, at, o, d, st);
-            case 64: return run_vec<float, 64, 4>(v, shapes, lsi, lo, at, o, d, st);
-            }
-        }
-        return run_generic<float, float>(value, shapes, lsi, loc, attn, out, d, st);
-    }
-    if (use_vec<__nv_bfloat16>(d, vec_ok)) {
-        const __nv_bfloat16 *v = (const __nv_bfloat16 *)value;
-        const float *lo = (const float *)loc, *at = (const float *)attn;
-        __nv_bfloat16 *o = (__nv_bfloat16 *)out;
-        switch (d.D) {
-        case 32: return run_vec<__nv_bfloat16, 32, 4>(v, shapes, lsi, lo, at, o, d, st);
-        case 64: return run_vec<__nv_bfloat16, 64, 4>(v, shapes, lsi, lo, at, o, d, st);
-        }
-    }
+    if (dt == DType::F32) return run_generic<float, float>(value, shapes, lsi, loc, attn, out, d, st);
     return run_generic<__nv_bfloat16, float>(value, shapes, lsi, loc, attn, out, d, st);
 }
 

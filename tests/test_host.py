@@ -56,11 +56,11 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert _lib.last_error() == ""
     with pytest.raises(ValueError):
         _lib.set_tuning("no_such_knob", 1)
-    _lib.set_tuning("block_threads", 128)
-    assert _lib.get_tuning("block_threads") == 128
-    _lib.set_tuning("block_threads", -1)
+    _lib.set_tuning("fwd_pipe", 6)
+    assert _lib.get_tuning("fwd_pipe") == 6
+    _lib.set_tuning("fwd_pipe", -1)
     assert lib.msda_describe_forward(32, 0, 32, 4, 4) == b"fwd_rec_f32"
-    assert lib.msda_describe_backward(32, 0, 32, 4, 4) == b"bwd_vec_f32"
+    assert lib.msda_describe_backward(32, 0, 32, 4, 4) == b"bwd_rec_f32"
     assert lib.msda_describe_backward(32, 0, 32, 4, 3) == b"bwd_rec_f32"
     assert lib.msda_describe_backward(32, 1, 32, 4, 4) == b"bwd_rec_bf16"
     assert lib.msda_describe_forward(64, 0, 32, 4, 4) == b"fwd_generic_f64"

@@ -190,35 +190,35 @@ def test_kernels_vs_oracle(msda, case, dtype):
     check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=str(case))
 
 
-@pytest.mark.parametrize("order", [0, 1, 10, 11])
-@pytest.mark.parametrize("threads", [64, 128, 256, 512])
-def test_every_launch_variant_is_correct(msda, order, threads):
+@pytest.mark.parametrize("order", [10, 11, 99])
+def test_every_launch_variant_is_correct(msda, order):
+    """work order 0 / 1 of the record kernels and the generic kernels on a vectorisable shape"""
     value, sh, lsi, loc, attn, grad_out = _random_case(7, [(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 203, 4)
     L = msda._lib
     try:
-        L.set_tuning("fwd_variant", order); L.set_tuning("bwd_variant", order); L.set_tuning("block_threads", threads)
-        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.float32, label=f"order{order} t{threads}")
-        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.bfloat16, label=f"order{order} t{threads}")
+        L.set_tuning("fwd_variant", order); L.set_tuning("bwd_variant", order)
+        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.float32, label=f"order{order}")
+        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.bfloat16, label=f"order{order}")
     finally:
-        L.set_tuning("fwd_variant", -1); L.set_tuning("bwd_variant", -1); L.set_tuning("block_threads", -1)
+        L.set_tuning("fwd_variant", -1); L.set_tuning("bwd_variant", -1)
 
 
-@pytest.mark.parametrize("pipe", [3, 5, 6, 14, 15, 16])
+@pytest.mark.parametrize("pipe", [3, 4, 5, 6, 14, 15, 16])
 def test_record_kernel_launch_flavours(msda, pipe):
     """fwd_pipe / bwd_pipe select register caps and the compacting forward; all must agree with the oracle."""
     L = msda._lib
     try:
-        L.set_tuning("fwd_pipe", pipe); L.set_tuning("bwd_variant", 11); L.set_tuning("bwd_pipe", pipe if pipe < 5 else 2)
+        L.set_tuning("fwd_pipe", pipe); L.set_tuning("bwd_pipe", pipe if pipe < 5 else (1 if pipe < 10 else 2))
         for case in ([(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 203, 4), ([(9, 7), (5, 4), (3, 3)], 2, 4, 32, 19, 3):
             shapes, N, M, D, Lq, P = case
             value, sh, lsi, loc, attn, grad_out = _random_case(21, shapes, N, M, D, Lq, P)
             for dtype in (torch.float32, torch.bfloat16):
                 check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=f"pipe{pipe} {case}")
     finally:
-        L.set_tuning("fwd_pipe", -1); L.set_tuning("bwd_variant", -1); L.set_tuning("bwd_pipe", -1)
+        L.set_tuning("fwd_pipe", -1); L.set_tuning("bwd_pipe", -1)
 
 
-def test_generic_and_vector_kernels_agree(msda):
+def test_generic_and_record_kernels_agree(msda):
     """variant 99 forces the generic kernels for a vectorisable shape."""
     value, sh, lsi, loc, attn, grad_out = _random_case(8, [(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 77, 4)
     L = msda._lib

@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import monosowa_b200 as msda  # noqa: E402
 from monosowa_b200 import workloads as W  # noqa: E402
 
-KEYS = ("fwd_variant", "bwd_variant", "block_threads", "fwd_pipe", "bwd_pipe")
+KEYS = ("fwd_variant", "bwd_variant", "fwd_pipe", "bwd_pipe")
 
 
 def timeit(fn, iters):
