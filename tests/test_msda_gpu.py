@@ -218,6 +218,25 @@ def test_record_kernel_launch_flavours(msda, pipe):
         L.set_tuning("fwd_pipe", -1); L.set_tuning("bwd_pipe", -1)
 
 
+def _fuzz_case(i):
+    g = torch.Generator().manual_seed(9000 + i)
+    r = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    L = r(1, 5)
+    shapes = [(r(1, 9), r(1, 11)) for _ in range(L)]
+    D = [16, 32, 64, 32, 32, 8, 24, 30, 5][r(0, 8)]
+    dtype = [torch.float32, torch.float32, torch.bfloat16, torch.float64][r(0, 3)]
+    return shapes, r(1, 3), [1, 2, 3, 4, 8][r(0, 4)], D, r(1, 70), r(1, 6), dtype
+
+
+@pytest.mark.parametrize("i", range(32))
+def test_fuzz_random_shapes(msda, i):
+    """seeded random (levels, N, M, D, Lq, P, dtype): record kernels for D in {16,32,64} (any L*P, ragged
+    batches, 1x1 levels), generic kernels otherwise; ~25 % of the locations outside [0,1]."""
+    shapes, N, M, D, Lq, P, dtype = _fuzz_case(i)
+    value, sh, lsi, loc, attn, grad_out = _random_case(9100 + i, shapes, N, M, D, Lq, P, spread=1.5, shift=-0.25)
+    check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=f"fuzz{i} {shapes} N{N} M{M} D{D} Lq{Lq} P{P}")
+
+
 def test_generic_and_record_kernels_agree(msda):
     """variant 99 forces the generic kernels for a vectorisable shape."""
     value, sh, lsi, loc, attn, grad_out = _random_case(8, [(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 77, 4)
