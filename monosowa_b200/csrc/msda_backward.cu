@@ -63,7 +63,7 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     uint32_t *grp = s_rec + (threadIdx.x >> 5) * RL::WARP_WORDS + k * RL::GROUP_WORDS;
 
     float g[4];
-    Vec4<VT>::load(grad_out + qm * D + gl * kChannelsPerLane, g);
+    Vec4<VT>::load_stream(grad_out + qm * D + gl * kChannelsPerLane, g);
 
     float aw[kMaxBatches];                          // FUSED: softmax weights of this lane's samples ...
     float pa[kMaxBatches], pg[kMaxBatches];         // ... and, per processed batch, (a, d out / d a)
@@ -160,12 +160,12 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
             if constexpr (FUSED) {
                 // d loc / d offset = 1 / (W, H); outside samples have gx = gy = 0 (Wf = Hf = 0 there)
                 const float ox = gm.live ? __fdiv_rn(gx, gm.Wf) : 0.f, oy = gm.live ? __fdiv_rn(gy, gm.Hf) : 0.f;
-                *reinterpret_cast<float2 *>(grad_loc + 2 * si) = make_float2(ox, oy);
+                __stcs(reinterpret_cast<float2 *>(grad_loc + 2 * si), make_float2(ox, oy));
                 pa[0] = pa[1]; pa[1] = pa[2]; pa[2] = pa[3]; pa[3] = a_cur;       // queue of (a, grad_a), newest last
                 pg[0] = pg[1]; pg[1] = pg[2]; pg[2] = pg[3]; pg[3] = ga;
             } else {
-                *reinterpret_cast<float2 *>(grad_loc + 2 * si) = make_float2(gx, gy);
-                grad_attn[si] = ga;
+                __stcs(reinterpret_cast<float2 *>(grad_loc + 2 * si), make_float2(gx, gy));
+                __stcs(grad_attn + si, ga);
             }
         } else if constexpr (FUSED) {
             pa[0] = pa[1]; pa[1] = pa[2]; pa[2] = pa[3]; pa[3] = 0.f;

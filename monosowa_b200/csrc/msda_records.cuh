@@ -36,7 +36,12 @@ struct Vec4<float> {
     }
     static __device__ __forceinline__ void store(float *p, const float (&f)[4])
     {
-        *reinterpret_cast<float4 *>(p) = make_float4(f[0], f[1], f[2], f[3]);
+        __stcs(reinterpret_cast<float4 *>(p), make_float4(f[0], f[1], f[2], f[3]));      // written once, never re-read here
+    }
+    static __device__ __forceinline__ void load_stream(const float *p, float (&f)[4])
+    {
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(p));
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
     }
 };
 
@@ -54,8 +59,16 @@ struct Vec4<__nv_bfloat16> {
     {
         const __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]);
         const __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
-        *reinterpret_cast<uint2 *>(p) =
-            make_uint2(*reinterpret_cast<const unsigned *>(&a), *reinterpret_cast<const unsigned *>(&b));
+        __stcs(reinterpret_cast<uint2 *>(p),
+               make_uint2(*reinterpret_cast<const unsigned *>(&a), *reinterpret_cast<const unsigned *>(&b)));
+    }
+    static __device__ __forceinline__ void load_stream(const __nv_bfloat16 *p, float (&f)[4])
+    {
+        const uint2 v = __ldcs(reinterpret_cast<const uint2 *>(p));
+        f[0] = __uint_as_float(v.x << 16);
+        f[1] = __uint_as_float(v.x & 0xffff0000u);
+        f[2] = __uint_as_float(v.y << 16);
+        f[3] = __uint_as_float(v.y & 0xffff0000u);
     }
 };
 
@@ -93,9 +106,10 @@ __device__ __forceinline__ SampleIn fetch_sample(bool has, const float *__restri
 {
     SampleIn in{0.f, 0.f, 0.f};
     if (has) {
-        const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + sample_index);
+        // read-once streams: keep them from displacing the value lines that the gather re-uses in L1/L2
+        const float2 xy = __ldcs(reinterpret_cast<const float2 *>(loc) + sample_index);
         in.x = xy.x; in.y = xy.y;
-        in.a = __ldg(attn + sample_index);
+        in.a = __ldcs(attn + sample_index);
     }
     return in;
 }
@@ -158,7 +172,7 @@ __device__ __forceinline__ SampleIn fetch_sample_fused(bool has, const float *__
 {
     SampleIn in{0.f, 0.f, 0.f};
     if (has) {
-        const float2 o = __ldg(reinterpret_cast<const float2 *>(offsets) + sample_index);
+        const float2 o = __ldcs(reinterpret_cast<const float2 *>(offsets) + sample_index);
         const float2 r = __ldg(reinterpret_cast<const float2 *>(ref) + ref_index);
         const LevelInfo li = s_lv[l];
         in.x = r.x + __fdiv_rn(o.x, (float)li.W);

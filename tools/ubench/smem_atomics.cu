@@ -76,11 +76,26 @@ __global__ void __launch_bounds__(256) k(float *gout, long long *cycles)
             float4 o = *reinterpret_cast<float4 *>(p);
             *reinterpret_cast<float4 *>(p) = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
         }
+        if (MODE == 5) {   // TMA bulk reduce: stage the 128-B row in smem, one cp.reduce.async.bulk per row
+            float *stage = tile + ((threadIdx.x >> 5) * 2 + (it & 1)) * 128 + (lane >> 3) * 32;   // per-warp double buffer
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            *reinterpret_cast<float4 *>(stage + gl * 4) = v;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (gl == 0) {
+                float *g = gout + ((size_t)blockIdx.x % 592) * ROWS * 32 + row * 32;
+                unsigned saddr = (unsigned)__cvta_generic_to_shared(stage);
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 128;" ::"l"(g), "r"(saddr) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         if (MODE == 4) {   // REDG.128 to a global tile of the same shape (per-CTA distinct region)
             float *g = gout + ((size_t)blockIdx.x % 592) * ROWS * 32 + row * 32 + gl * 4;
             asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
         }
     }
+    if (MODE == 5) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncthreads();
     long long t1 = clock64();
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
@@ -121,5 +136,6 @@ int main()
     run<1>("CAS64 loop x2", gout, cyc, nsm);
     run<2>("CAS128 loop x1", gout, cyc, nsm);
     run<4>("REDG.128 global", gout, cyc, nsm);
+    run<5>("TMA bulk reduce 128 B/row", gout, cyc, nsm);
     return 0;
 }
