@@ -356,6 +356,55 @@ def test_config4_large_image_shapes(msda):
                              d["attn"].double(), d["grad_out"].double(), wl.dtype, label=wl.name)
 
 
+def test_beyond_int32_indexing(msda, cuda_device):
+    """Maximum sizes: value with 2^31 + 4096 elements (8.6 GB).  The reference kernels index with int32
+    (ms_deform_im2col_cuda.cuh:47-53) and would overflow here; this library switches to its 64-bit generic
+    kernels.  All samples of level 0 fall into its bottom-right corner, so the expected result is the oracle
+    on a cropped problem (last 8 rows x 12 columns of level 0 + the whole level 1) with re-normalised
+    locations; everything outside the crop must receive exactly zero gradient."""
+    dev = cuda_device
+    H, W, M, D, Lq, P, CH, CW = 2048, 4096, 8, 32, 24, 3, 8, 12
+    g = torch.Generator(device=dev).manual_seed(4242)
+    sh = torch.tensor([[H, W], [4, 4]], device=dev); lsi = torch.tensor([0, H * W], device=dev)
+    S = H * W + 16
+    assert S * M * D >= 2 ** 31
+    value = torch.randn(1, S, M, D, generator=g, device=dev)
+    px = torch.rand(1, Lq, M, 1, P, generator=g, device=dev) * 8.8 + (W - 9)        # up to 0.3 px beyond the right edge
+    py = torch.rand(1, Lq, M, 1, P, generator=g, device=dev) * 4.8 + (H - 5)
+    loc0 = torch.stack([(px + 0.5) / W, (py + 0.5) / H], -1)
+    loc1 = torch.rand(1, Lq, M, 1, P, 2, generator=g, device=dev) * 1.4 - 0.2
+    loc = torch.cat([loc0, loc1], 3).contiguous().requires_grad_(True)
+    attn = torch.softmax(torch.randn(1, Lq, M, 2 * P, generator=g, device=dev), -1).view(1, Lq, M, 2, P).requires_grad_(True)
+    grad_out = torch.randn(1, Lq, M * D, generator=g, device=dev)
+    v = value.requires_grad_(True)
+    assert msda._lib.lib.msda_describe_forward(32, 0, D, 2, P) == b"fwd_rec_f32"     # the shape alone would vectorise
+    out = msda.MSDeformAttnFunction.apply(v, sh, lsi, loc, attn, 64)
+    out.backward(grad_out)
+    torch.cuda.synchronize()
+    # cropped fp64 problem, pixel coordinates taken exactly as the fp32 kernel forms them
+    l32 = loc.detach()
+    pxk = (l32[..., 0, :, 0] * W).float() - 0.5
+    pyk = (l32[..., 0, :, 1] * H).float() - 0.5
+    locc0 = torch.stack([(pxk.double() - (W - CW) + 0.5) / CW, (pyk.double() - (H - CH) + 0.5) / CH], -1)[:, :, :, None]
+    locc = torch.cat([locc0, l32[..., 1:2, :, :].double()], 3).cpu()
+    lvl0 = value.detach()[0, :H * W].view(H, W, M, D)[H - CH:, W - CW:].reshape(1, CH * CW, M, D)
+    vcrop = torch.cat([lvl0, value.detach()[:, H * W:]], 1).double().cpu()
+    shc, lsic = torch.tensor([[CH, CW], [4, 4]]), torch.tensor([0, CH * CW])
+    ref_out = O.forward_c(vcrop, shc, lsic, locc, attn.detach().double().cpu())
+    rgv, rgl, rga = O.backward_c(vcrop, shc, lsic, locc, attn.detach().double().cpu(), grad_out.double().cpu())
+    assert O.rel_l2(out, ref_out) < 1e-5
+    assert O.rel_l2(attn.grad, rga) < 1e-4
+    gv = v.grad[0]
+    gcrop = torch.cat([gv[:H * W].view(H, W, M, D)[H - CH:, W - CW:].reshape(CH * CW, M, D), gv[H * W:]], 0)
+    assert O.rel_l2(gcrop, rgv[0]) < 1e-4
+    assert abs(gv.double().abs().sum().item() - gcrop.double().abs().sum().item()) < 1e-6 * gcrop.double().abs().sum().item()
+    # d/dloc of level 0 differs from the cropped problem by the normalisation ratio (W/CW, H/CH)
+    keep = ~O.pixel_boundary_mask(locc, shc, eps_px=2e-3)            # fp32 pixel coordinates near 4096 resolve 2.4e-4 px
+    scale = torch.tensor([W / CW, H / CH], dtype=torch.float64)
+    rgl_full = rgl.clone(); rgl_full[..., 0, :, :] *= scale
+    assert O.rel_l2(loc.grad.cpu()[keep], rgl_full[keep]) < 1e-4
+
+
 # --------------------------------------------------------------------------------------------
 # 5. against the reference's own CUDA kernels recompiled for sm_100a (oracle/_ref)
 # --------------------------------------------------------------------------------------------
