@@ -36,7 +36,9 @@ class Workload:
     head_dim: int = 32
     points: int = 4
     dtype: torch.dtype = torch.float32
-    loc_mode: str = "model"      # "model" (pixel-centre refs + N(0,2px) offsets) or "uniform"
+    loc_mode: str = "model"      # "model" (pixel-centre refs + N(0,2px) offsets), "uniform", or "init"
+                                 # ("init": the module's initial offset pattern, identical for all queries
+                                 #  -- reference ms_deform_attn.py:106-115; "init+noise": plus N(0, 0.5 px))
     seed: int = 1234
     note: str = ""
     S: int = field(init=False)
@@ -118,7 +120,17 @@ def make_inputs(wl: Workload, device="cpu", seed=None, requires_grad=False):
             ref = encoder_reference_points(wl.shapes, dev, ct)[None].expand(N, -1, -1, -1)
         else:
             ref = torch.rand(N, Lq, 1, 2, generator=g, device=dev, dtype=ct).mul_(0.9).add_(0.05).expand(-1, -1, L, -1)
-        off_px = torch.randn(N, Lq, M, L, P, 2, generator=g, device=dev, dtype=ct).mul_(2.0)
+        if wl.loc_mode.startswith("init"):
+            theta = torch.arange(M, device=dev, dtype=ct) * (2.0 * math.pi / M)
+            ring = torch.stack([theta.cos(), theta.sin()], -1)
+            ring = ring / ring.abs().max(-1, keepdim=True)[0]                                   # (M, 2)
+            steps = torch.arange(1, P + 1, device=dev, dtype=ct)
+            off_px = (ring[:, None, None, :] * steps[None, None, :, None]).expand(M, L, P, 2)
+            off_px = off_px[None, None].expand(N, Lq, M, L, P, 2)
+            if wl.loc_mode == "init+noise":
+                off_px = off_px + torch.randn(N, Lq, M, L, P, 2, generator=g, device=dev, dtype=ct).mul_(0.5)
+        else:
+            off_px = torch.randn(N, Lq, M, L, P, 2, generator=g, device=dev, dtype=ct).mul_(2.0)
         loc = ref[:, :, None, :, None, :] + off_px / wh[None, None, None, :, None, :]
     attn = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g, device=dev, dtype=ct), -1).view(N, Lq, M, L, P)
     grad_out = torch.randn(N, Lq, M * D, generator=g, device=dev, dtype=ct).to(wl.dtype)
