@@ -30,7 +30,7 @@ namespace msda {
 // FUSED: `loc` = raw sampling offsets, `attn` = raw logits, `ref` = (N,Lq,L,2)
 // reference points; `grad_loc` receives d/d offsets = grad_loc / (W,H) and `grad_attn` receives
 // d/d logits = a * (grad_a - sum_j a_j grad_a_j)  (softmax backward over the L*P samples).
-template <typename VT, int D, int MINB, bool FUSED = false>
+template <typename VT, int D, int MINB, bool FUSED = false, int LOADH = 0>
 __global__ void __launch_bounds__(256, MINB)
 bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ lsi, const float *__restrict__ loc,
@@ -110,10 +110,10 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
                 if (d.S > 0) {
                     float v00[4], v01[4], v10[4], v11[4];
-                    Vec4<VT>::load(vimg + off.x, v00);
-                    Vec4<VT>::load(vimg + off.y, v01);
-                    Vec4<VT>::load(vimg + off.z, v10);
-                    Vec4<VT>::load(vimg + off.w, v11);
+                    Vec4<VT>::template gather<LOADH>(vimg + off.x, v00);
+                    Vec4<VT>::template gather<LOADH>(vimg + off.y, v01);
+                    Vec4<VT>::template gather<LOADH>(vimg + off.z, v10);
+                    Vec4<VT>::template gather<LOADH>(vimg + off.w, v11);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         t[4 * u] += g[c] * v00[c];
@@ -293,6 +293,16 @@ int run_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const 
     case 1: MSDA_BWD_REC(1); break;
     case 2: MSDA_BWD_REC(2); break;
     case 4: MSDA_BWD_REC(4); break;
+    case 13:
+        bwd_rec_kernel<VT, D, 3, false, 1><<<(unsigned)grid, threads, 0, st>>>(
+            (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,
+            (float *)gv, (float *)gl, (float *)ga, d, order);
+        break;
+    case 23:
+        bwd_rec_kernel<VT, D, 3, false, 2><<<(unsigned)grid, threads, 0, st>>>(
+            (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,
+            (float *)gv, (float *)gl, (float *)ga, d, order);
+        break;
     default: if (D <= 32) MSDA_BWD_REC(3); else MSDA_BWD_REC(1); break;
     }
 #undef MSDA_BWD_REC

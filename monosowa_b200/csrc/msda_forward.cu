@@ -23,7 +23,7 @@ namespace msda {
 // ------------------------------------------------------------------------------------------------
 // FUSED: `loc` holds the raw sampling offsets, `attn` the raw attention logits and
 // `ref` the (N,Lq,L,2) reference points; locations and softmax weights are formed in registers.
-template <typename VT, int D, int MINB, bool COMPACT, bool FUSED = false>
+template <typename VT, int D, int MINB, bool COMPACT, bool FUSED = false, int LOADH = 0>
 __global__ void __launch_bounds__(256, MINB)
 fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ lsi, const float *__restrict__ loc,
@@ -87,10 +87,10 @@ fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                     const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
                     const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
                     float v00[4], v01[4], v10[4], v11[4];
-                    Vec4<VT>::load(vimg + off.x, v00);
-                    Vec4<VT>::load(vimg + off.y, v01);
-                    Vec4<VT>::load(vimg + off.z, v10);
-                    Vec4<VT>::load(vimg + off.w, v11);
+                    Vec4<VT>::template gather<LOADH>(vimg + off.x, v00);
+                    Vec4<VT>::template gather<LOADH>(vimg + off.y, v01);
+                    Vec4<VT>::template gather<LOADH>(vimg + off.z, v10);
+                    Vec4<VT>::template gather<LOADH>(vimg + off.w, v11);
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
                         acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
@@ -106,10 +106,10 @@ fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
                 const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
                 float v00[4], v01[4], v10[4], v11[4];
-                Vec4<VT>::load(vimg + off.x, v00);
-                Vec4<VT>::load(vimg + off.y, v01);
-                Vec4<VT>::load(vimg + off.z, v10);
-                Vec4<VT>::load(vimg + off.w, v11);
+                Vec4<VT>::template gather<LOADH>(vimg + off.x, v00);
+                Vec4<VT>::template gather<LOADH>(vimg + off.y, v01);
+                Vec4<VT>::template gather<LOADH>(vimg + off.z, v10);
+                Vec4<VT>::template gather<LOADH>(vimg + off.w, v11);
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
@@ -196,16 +196,26 @@ int run_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const fl
     // fwd_pipe = requested minimum CTAs/SM (register cap 64K / (256 * MINB)); trades ILP for TLP
 #define MSDA_FWD_REC(MINB, COMPACT) \
     fwd_rec_kernel<VT, D, MINB, COMPACT><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order)
-    // Default, measured on B200 at configs[1] (profiles/r01_v2_compact_sweep.jsonl): fp32 -- compacting
-    // loop at <= 48 registers (5 CTAs/SM) 0.593 ms; bf16 -- unrolled loop at <= 40 registers 0.493 ms.
-    // All flavours sit within ~5 % of each other: the kernel is bound by L1 data-pipe wavefronts.
+    // Default, measured on B200 at configs[1] (profiles/r01_v2_compact_sweep.jsonl, r01_loadhint_sweep.jsonl):
+    // fp32 -- compacting loop at <= 48 registers (5 CTAs/SM) with L1::no_allocate gathers 0.529 ms (0.592 with
+    // allocating loads: L1 fills compete with the gather for the data pipe, hits are still served);
+    // bf16 -- unrolled loop at <= 40 registers with allocating loads 0.493 ms (hints make no difference there).
     int flavour = tuning().fwd_pipe;
-    if (flavour < 0) flavour = sizeof(VT) == 4 ? 15 : 6;
+    if (flavour < 0) flavour = sizeof(VT) == 4 ? 25 : 6;
     switch (flavour) {
     case 3: MSDA_FWD_REC(3, false); break;
     case 5: MSDA_FWD_REC(5, false); break;
     case 6: MSDA_FWD_REC(6, false); break;
     case 15: MSDA_FWD_REC(5, true); break;
+#define MSDA_FWD_REC_H(MINB, COMPACT, H) \
+    fwd_rec_kernel<VT, D, MINB, COMPACT, false, H><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order)
+    case 25: MSDA_FWD_REC_H(5, true, 1); break;
+    case 35: MSDA_FWD_REC_H(5, true, 2); break;
+    case 26: MSDA_FWD_REC_H(6, false, 1); break;
+    case 36: MSDA_FWD_REC_H(6, false, 2); break;
+    case 24: MSDA_FWD_REC_H(4, true, 1); break;
+    case 27: MSDA_FWD_REC_H(6, true, 1); break;
+#undef MSDA_FWD_REC_H
     case 14: MSDA_FWD_REC(4, true); break;
     case 16: MSDA_FWD_REC(6, true); break;
     default: MSDA_FWD_REC(4, false); break;
@@ -263,7 +273,7 @@ int run_rec_fused(const void *value, const int64_t *shapes, const int64_t *lsi, 
     if (d.L * d.P > kMaxBatches * G) return kUnsupported;
     const long grid = grid_for(d, 1, 32 / G, 256);
     if (sizeof(VT) == 4)
-        fwd_rec_kernel<VT, D, 5, true, true><<<(unsigned)grid, 256, 0, st>>>(
+        fwd_rec_kernel<VT, D, 5, true, true, 1><<<(unsigned)grid, 256, 0, st>>>(
             (const VT *)value, shapes, lsi, (const float *)offsets, (const float *)logits, (VT *)out, d, 1, (const float *)ref);
     else
         fwd_rec_kernel<VT, D, 6, false, true><<<(unsigned)grid, 256, 0, st>>>(

@@ -11,7 +11,8 @@
 //   * an invalid corner keeps a clamped (in-map) address and a zero weight -- the clamped pixel is
 //     always one of the sample's own valid corners;
 //   * a sample outside the (-1,H)x(-1,W) window, or past L*P, points at element 0 of the image
-//     (one hot L1 line) with four zero weights.
+//     (one hot L1 line -- these kernels gather with L1 allocation; measured: pointing such records at
+//     per-query rows, or bypassing L1, is slower) with four zero weights.
 // For finite `value` this is exactly the reference's skip logic (ms_deform_im2col_cuda.cuh:56-80,
 // 288); a NaN/Inf stored at pixel 0 of a head would additionally reach queries that have outside
 // samples (0 * NaN), which the reference's branches avoid -- documented in DESIGN.md.
@@ -38,6 +39,21 @@ struct Vec4<float> {
     {
         __stcs(reinterpret_cast<float4 *>(p), make_float4(f[0], f[1], f[2], f[3]));      // written once, never re-read here
     }
+    // gather loads of `value` rows.  H = 0: ld.global.nc (allocate in L1); 1: L1::no_allocate (hits are still
+    // served by L1, misses do not evict); 2: ld.global.cg (L2 only)
+    template <int H>
+    static __device__ __forceinline__ void gather(const float *p, float (&f)[4])
+    {
+        if constexpr (H == 1) {
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "l"(p));
+        } else if constexpr (H == 2) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(p));
+            f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+        } else {
+            load(p, f);
+        }
+    }
     static __device__ __forceinline__ void load_stream(const float *p, float (&f)[4])
     {
         const float4 v = __ldcs(reinterpret_cast<const float4 *>(p));
@@ -61,6 +77,22 @@ struct Vec4<__nv_bfloat16> {
         const __nv_bfloat162 b = __floats2bfloat162_rn(f[2], f[3]);
         __stcs(reinterpret_cast<uint2 *>(p),
                make_uint2(*reinterpret_cast<const unsigned *>(&a), *reinterpret_cast<const unsigned *>(&b)));
+    }
+    template <int H>
+    static __device__ __forceinline__ void gather(const __nv_bfloat16 *p, float (&f)[4])
+    {
+        uint2 v;
+        if constexpr (H == 1) {
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+        } else if constexpr (H == 2) {
+            v = __ldcg(reinterpret_cast<const uint2 *>(p));
+        } else {
+            v = __ldg(reinterpret_cast<const uint2 *>(p));
+        }
+        f[0] = __uint_as_float(v.x << 16);
+        f[1] = __uint_as_float(v.x & 0xffff0000u);
+        f[2] = __uint_as_float(v.y << 16);
+        f[3] = __uint_as_float(v.y & 0xffff0000u);
     }
     static __device__ __forceinline__ void load_stream(const __nv_bfloat16 *p, float (&f)[4])
     {

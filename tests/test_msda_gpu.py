@@ -203,12 +203,12 @@ def test_every_launch_variant_is_correct(msda, order):
         L.set_tuning("fwd_variant", -1); L.set_tuning("bwd_variant", -1)
 
 
-@pytest.mark.parametrize("pipe", [3, 4, 5, 6, 14, 15, 16])
+@pytest.mark.parametrize("pipe", [3, 4, 5, 6, 14, 15, 16, 24, 25, 26, 27, 35, 36])
 def test_record_kernel_launch_flavours(msda, pipe):
     """fwd_pipe / bwd_pipe select register caps and the compacting forward; all must agree with the oracle."""
     L = msda._lib
     try:
-        L.set_tuning("fwd_pipe", pipe); L.set_tuning("bwd_pipe", pipe if pipe < 5 else (1 if pipe < 10 else 2))
+        L.set_tuning("fwd_pipe", pipe); L.set_tuning("bwd_pipe", {3: 3, 4: 4, 5: 1, 6: 2, 25: 13, 35: 23}.get(pipe, -1))
         for case in ([(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 203, 4), ([(9, 7), (5, 4), (3, 3)], 2, 4, 32, 19, 3):
             shapes, N, M, D, Lq, P = case
             value, sh, lsi, loc, attn, grad_out = _random_case(21, shapes, N, M, D, Lq, P)
