@@ -108,6 +108,10 @@ def main():
     ap.add_argument("--op", default="ours", choices=["ours", "ref_cuda"])
     ap.add_argument("--logging", default="faithful", choices=["faithful", "lean"])
     ap.add_argument("--profile-msda", action="store_true", help="kineto pass: MSDA kernels' share of the step")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="infer: model.eval() forward only (50 queries), as tester_helper.py:80-99")
+    ap.add_argument("--amp", default="none", choices=["none", "bf16"],
+                    help="bf16: autocast around the model forward (beyond the reference, which trains in fp32)")
     args = ap.parse_args()
 
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -150,9 +154,32 @@ def main():
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=unused,
                                                         gradient_as_bucket_view=True)
 
-    def step(i):
+    amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.amp == "bf16")
+
+    def to_f32(o):
+        if isinstance(o, torch.Tensor):
+            return o.float() if o.is_floating_point() else o
+        if isinstance(o, dict):
+            return {k: to_f32(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return type(o)(to_f32(v) for v in o)
+        return o
+
+    if args.mode == "infer":
+        model.eval()
+
+        def step(i):                                             # tester_helper.py:94-99
+            with torch.no_grad(), amp:
+                outputs = net(images, calibs, targets, img_sizes, dn_args=None)
+            return outputs["pred_logits"].float().sum()
+    else:
+        step = None
+
+    def train_step(i):
         optimizer.zero_grad()
-        outputs = net(images, calibs, targets, img_sizes, dn_args=None)
+        with amp:
+            outputs = net(images, calibs, targets, img_sizes, dn_args=None)
+        outputs = to_f32(outputs)
         ld = criterion(outputs, targets, None, None)
         loss = sum(ld[k] * weight_dict[k] for k in ld.keys() if k in weight_dict)
         if args.logging == "faithful" or i % 30 == 0:           # trainer_helper.py:150-158
@@ -161,6 +188,9 @@ def main():
         loss.backward()
         optimizer.step()
         return loss
+
+    if step is None:
+        step = train_step
 
     for i in range(args.warmup):
         loss = step(i)
@@ -205,12 +235,12 @@ def main():
     if rank == 0:
         med, mean, wallms = ms.tolist()
         print(json.dumps({
-            "metric": "MonoDETR train img/s", "value": args.batch * world / (mean * 1e-3), "unit": "img/s", "n_gpus": world,
+            "metric": "MonoDETR train img/s" if args.mode == "train" else "MonoDETR inference img/s", "value": args.batch * world / (mean * 1e-3), "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean, "ms_per_step_median": med,
             "ms_per_step_wall": wallms, "scaling": "weak", "higher_is_better": True, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE.json configs[3]: unmodified reference MonoDETR (ResNet-50, 3 enc + 3 dec layers) + "
                                    "SetCriterion + reference AdamW, synthetic KITTI batch", "batch_per_gpu": args.batch,
-                       "global_batch": args.batch * world, "image": [384, 1280], "msda_op": args.op, "logging": args.logging,
+                       "global_batch": args.batch * world, "image": [384, 1280], "msda_op": args.op, "logging": args.logging, "mode": args.mode, "amp": args.amp,
                        "parallelism": f"ddp{world}", "trainable_params": n_params},
             "loss": float(loss), "msda": share}), flush=True)
     if world > 1:
