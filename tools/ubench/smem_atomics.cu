@@ -90,12 +90,30 @@ __global__ void __launch_bounds__(256) k(float *gout, long long *cycles)
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        if (MODE == 6) {   // split: groups 0-1 of each warp reduce through TMA, groups 2-3 through REDG.128
+            float *stage = tile + ((threadIdx.x >> 5) * 2 + (it & 1)) * 128 + (lane >> 3) * 32;
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            float *g = gout + ((size_t)blockIdx.x % 592) * ROWS * 32 + row * 32;
+            if (lane < 16) *reinterpret_cast<float4 *>(stage + gl * 4) = v;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < 16) {
+                if (gl == 0) {
+                    unsigned saddr = (unsigned)__cvta_generic_to_shared(stage);
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 128;" ::"l"(g), "r"(saddr) : "memory");
+                }
+            } else {
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(g + gl * 4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         if (MODE == 4) {   // REDG.128 to a global tile of the same shape (per-CTA distinct region)
             float *g = gout + ((size_t)blockIdx.x % 592) * ROWS * 32 + row * 32 + gl * 4;
             asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
         }
     }
-    if (MODE == 5) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (MODE == 5 || MODE == 6) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncthreads();
     long long t1 = clock64();
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
@@ -137,5 +155,6 @@ int main()
     run<2>("CAS128 loop x1", gout, cyc, nsm);
     run<4>("REDG.128 global", gout, cyc, nsm);
     run<5>("TMA bulk reduce 128 B/row", gout, cyc, nsm);
+    run<6>("half TMA + half REDG.128", gout, cyc, nsm);
     return 0;
 }
