@@ -373,6 +373,8 @@ int launch_backward_fused(DType dt, const void *value, const int64_t *shapes, co
         if (e != cudaSuccess) return (int)e;
     }
     if ((long)d.N * d.Lq * d.M == 0) return 0;
+    if (binned_backward_applies(d, dt, true))
+        return launch_backward_binned(dt, value, shapes, lsi, offsets, logits, grad_out, gv, goff, glogit, d, ref, st);
 #define FUSED_ARGS value, shapes, lsi, ref, offsets, logits, grad_out, gv, goff, glogit, d, st
     if (dt == DType::F32) {
         switch (d.D) {
@@ -414,6 +416,8 @@ int launch_backward(DType dt, const void *value, const int64_t *shapes, const in
         if (e != cudaSuccess) return (int)e;
     }
     if ((long)d.N * d.Lq * d.M == 0) return 0;
+    if (binned_backward_applies(d, dt, vec_ok))
+        return launch_backward_binned(dt, value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, nullptr, st);
 #define ARGS value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st
     if (dt == DType::F64) return run_generic<double, double>(ARGS);
     if (dt == DType::F32 && use_rec(d, vec_ok)) return dispatch_rec<float>(ARGS);

@@ -1,0 +1,420 @@
+// msda_backward_binned.cu -- MSDA backward for long query sets: the grad_value contributions of the
+// COARSE feature levels are combined inside the SM before they leave it.
+//
+// Why: bwd_rec_kernel is bound by the reductions that leave the SM -- one 128-byte
+// REDG line per (sample, corner), ~5.3 cycles each.  On a feature pyramid half of those lines go to the
+// two coarsest levels, which are tiny: at the KITTI shape levels 2 and 3 hold 600 pixels per head but
+// receive 8 of the 16 samples of every query, so a block of 256 queries sends ~7000 reduction lines to
+// at most 600 distinct rows.  This kernel keeps those contributions on chip:
+//
+//   phase A  the record kernel's work (msda_backward.cu) for a chunk of QC consecutive queries of one
+//            head: gathers, partial dots, grad_loc / grad_attn, and the REDGs of the FINE levels.  For a
+//            sample on a coarse ("binned") level the owning lane instead drops a 16-byte entry
+//            {a, lx, ly, cell | rank} into shared memory and counts it in a histogram over the base-corner
+//            cells of the level -- a (H+1)x(W+1) lattice, the corner (y0, x0) ranges over [-1,H-1]x[-1,W-1].
+//            The chunk's grad_out rows are parked in shared memory as well.
+//   phase B  exclusive scan of the histogram, then a counting-sort permutation of the entry indices.
+//   phase C  one lane group per non-empty cell: all samples of a cell share their four corner pixels, so the
+//            group reads each sample's grad_out row once from shared memory, accumulates the four corner
+//            rows ((wy*wx)*a)*g in registers and sends FOUR REDG lines per touched cell per chunk.
+//
+// Which levels are binned is decided on the device from spatial_shapes (the host never reads them):
+// the coarsest levels while their cells fit kMaxBins, their samples fit kBinSamples per query and the
+// level has at most QC*P pixels (>= 4 updates per row on average).  If none qualifies the kernel is
+// the record kernel plus two block barriers.  Arithmetic: same products as the direct path,
+// ((wy*wx)*a)*g, accumulated per pixel in fp32 before the single global reduction (the reference
+// accumulates all of them with global atomics, ms_deform_im2col_cuda.cuh:125-152) -- covered by the
+// backward tolerance, which already allows for atomic ordering.
+#include "msda_common.cuh"
+#include "msda_records.cuh"
+
+namespace msda {
+
+namespace {
+
+constexpr int kBinSamples = 8;      // entry slots per (query, head): samples on binned levels
+constexpr int kMaxBins = 704;       // base-corner cells over all binned levels
+constexpr int kBinThreads = 256;
+constexpr unsigned kNoEntry = 0xffffffffu;
+constexpr int kBinMinQueries = 1024;  // below this the chunks are too few / too short to pay for the two extra phases
+
+template <int D>
+struct BinCfg {
+    static constexpr int G = D / kChannelsPerLane;
+    static constexpr int QPW = 32 / G;
+    static constexpr int QPI = (kBinThreads / 32) * QPW;          // queries per pass of the CTA's warps
+    static constexpr int QC = D <= 32 ? 256 : 128;                // queries per CTA
+    static constexpr int HIST_HALVES = kMaxBins + 2;              // 16-bit counters, packed two per word
+    static constexpr int HIST_WORDS = (HIST_HALVES + 1) / 2;
+    static constexpr int G_BYTES = QC * D * 4;
+    static constexpr int ENT_BYTES = QC * kBinSamples * 16;
+    static constexpr int HIST_BYTES = ((HIST_WORDS * 4 + 15) / 16) * 16;
+    static constexpr int REC_BYTES = (kBinThreads / 32) * RecordLayout<G>::WARP_WORDS * 4;
+    static constexpr int SMEM = G_BYTES + ENT_BYTES + HIST_BYTES + REC_BYTES;
+    static_assert(REC_BYTES >= QC * kBinSamples * 2, "the sorted index array aliases the record area");
+    static_assert(QC % QPI == 0, "chunk must be a whole number of passes");
+    static_assert(QC * kBinSamples < 65536, "entry indices are 16-bit");
+};
+
+struct BinPlan {
+    int lb;                          // first binned level (levels lb..L-1 are binned); L if none
+    int lbP;                         // lb * P: first binned sample index of a query
+    int nbs;                         // binned samples per query = (L - lb) * P
+    int nbins;                       // cells over all binned levels
+    int binbase[MSDA_MAX_LEVELS];    // first cell of each binned level
+};
+
+template <typename VT, int D, bool FUSED>
+__global__ void __launch_bounds__(kBinThreads, 3)
+bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+               const float *__restrict__ loc, const float *__restrict__ attn, const VT *__restrict__ grad_out,
+               float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn,
+               const Dims d, const float *__restrict__ ref, const int max_binned)
+{
+    using C = BinCfg<D>;
+    using RL = RecordLayout<C::G>;
+    constexpr int G = C::G, QPW = C::QPW, QPI = C::QPI, QC = C::QC;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *s_g = reinterpret_cast<float *>(smem);
+    uint4 *s_ent = reinterpret_cast<uint4 *>(smem + C::G_BYTES);
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + C::G_BYTES + C::ENT_BYTES);
+    uint32_t *s_rec = reinterpret_cast<uint32_t *>(smem + C::G_BYTES + C::ENT_BYTES + C::HIST_BYTES);
+    __shared__ LevelInfo s_lv[MSDA_MAX_LEVELS];
+    __shared__ BinPlan s_plan;
+    __shared__ int s_warp_tot[kBinThreads / 32];
+    __shared__ int s_next;
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < C::HIST_WORDS; i += kBinThreads) s_hist[i] = 0u;
+    stage_levels(s_lv, shapes, lsi, d.L);
+    if (tid == 0) {
+        BinPlan p;
+        p.lb = d.L;
+        int nbins = 0;
+        for (int l = d.L - 1; l >= 0; --l) {
+            const int H = s_lv[l].H, W = s_lv[l].W;
+            if (H < 0 || W < 0 || H > 8192 || W > 8192) break;
+            const int cells = (H + 1) * (W + 1);
+            if ((d.L - l) * d.P > max_binned || nbins + cells > kMaxBins || H * W > QC * d.P) break;
+            p.binbase[l] = nbins;
+            nbins += cells;
+            p.lb = l;
+        }
+        p.lbP = p.lb * d.P;
+        p.nbs = (d.L - p.lb) * d.P;
+        p.nbins = nbins;
+        s_plan = p;
+        s_next = 0;
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int gl = lane % G, k = lane / G;
+    const int n_chunks = (d.Lq + QC - 1) / QC;
+    const int m = (int)(blockIdx.x % d.M);
+    const long cr = blockIdx.x / d.M;
+    const int q0 = (int)(cr % n_chunks) * QC;
+    const int n = (int)(cr / n_chunks);
+
+    const int LP = d.L * d.P;
+    const int lbP = s_plan.lbP;
+    const long img = ((long)n * d.S * d.M + m) * D + gl * kChannelsPerLane;
+    const VT *vimg = value + img;
+    float *gvimg = grad_value + img;
+    const int xs = d.M * D;
+    uint32_t *grp = s_rec + warp * RL::WARP_WORDS + k * RL::GROUP_WORDS;
+
+    // ---- phase A --------------------------------------------------------------------------------
+    for (int it = 0; it < QC / QPI; ++it) {
+        const int qw = it * QPI + warp * QPW;            // first local query of this warp's pass
+        if (q0 + qw >= d.Lq) break;                      // whole warp past the end
+        const int ql = qw + k;
+        const bool qvalid = q0 + ql < d.Lq;
+        const long qm = ((long)n * d.Lq + (qvalid ? q0 + ql : q0)) * d.M + m;
+
+        float g[4];
+        Vec4<VT>::load_stream(grad_out + qm * D + gl * kChannelsPerLane, g);
+        *reinterpret_cast<float4 *>(s_g + ql * D + gl * kChannelsPerLane) = make_float4(g[0], g[1], g[2], g[3]);
+
+        float aw[kMaxBatches];
+        float pa[kMaxBatches], pg[kMaxBatches];
+        if constexpr (FUSED) {
+            group_softmax<G>(attn, qm * LP, LP, gl, qvalid, aw);
+#pragma unroll
+            for (int b = 0; b < kMaxBatches; ++b) pa[b] = pg[b] = 0.f;
+        }
+        auto fetch = [&](int sidx) -> SampleIn {
+            const bool has = qvalid && sidx < LP;
+            if constexpr (FUSED) {
+                const int l = has ? sidx / d.P : 0;
+                const SampleIn r = fetch_sample_fused(has, loc, ref, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l, aw[0]);
+                aw[0] = aw[1]; aw[1] = aw[2]; aw[2] = aw[3];
+                return r;
+            } else {
+                return fetch_sample(has, loc, attn, qm * LP + sidx);
+            }
+        };
+        SampleIn in = fetch(gl);
+        for (int b0 = 0; b0 < LP; b0 += G) {
+            const int sidx = b0 + gl;
+            const bool has = qvalid && sidx < LP;
+            const int l = sidx / d.P;
+            const SampleGeom gm = build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, has && d.S > 0, in, s_lv, l, xs);
+            const float a_cur = in.a;
+            if (has && sidx >= lbP) {
+                // binned level: park the sample instead of sending its four reduction lines to L2
+                uint4 e = make_uint4(0u, 0u, 0u, kNoEntry);
+                if (gm.live && gm.a != 0.f) {
+                    const int bin = s_plan.binbase[l] + gm.cell;
+                    const unsigned sh = (bin & 1) * 16;
+                    const unsigned old = atomicAdd(&s_hist[bin >> 1], 1u << sh);
+                    e = make_uint4(__float_as_uint(gm.a), __float_as_uint(gm.lx), __float_as_uint(gm.ly),
+                                   (unsigned)bin | (((old >> sh) & 0xffffu) << 16));
+                }
+                s_ent[ql * kBinSamples + (sidx - lbP)] = e;
+            }
+            __syncwarp();
+            in = fetch(sidx + G);
+
+            constexpr int GH = G / 2;
+            float th[2][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float t[4 * GH];
+#pragma unroll
+                for (int u = 0; u < GH; ++u) {
+                    const int s = h * GH + u;
+                    t[4 * u] = t[4 * u + 1] = t[4 * u + 2] = t[4 * u + 3] = 0.f;
+                    const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
+                    const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
+                    if (d.S > 0) {
+                        float v00[4], v01[4], v10[4], v11[4];
+                        Vec4<VT>::template gather<0>(vimg + off.x, v00);
+                        Vec4<VT>::template gather<0>(vimg + off.y, v01);
+                        Vec4<VT>::template gather<0>(vimg + off.z, v10);
+                        Vec4<VT>::template gather<0>(vimg + off.w, v11);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            t[4 * u] += g[c] * v00[c];
+                            t[4 * u + 1] += g[c] * v01[c];
+                            t[4 * u + 2] += g[c] * v10[c];
+                            t[4 * u + 3] += g[c] * v11[c];
+                        }
+                    }
+                    if (b0 + s < lbP) {                  // fine level (warp-uniform): direct reductions
+                        if (wa.x != 0.f) red_add_f32x4(gvimg + off.x, wa.x * g[0], wa.x * g[1], wa.x * g[2], wa.x * g[3]);
+                        if (wa.y != 0.f) red_add_f32x4(gvimg + off.y, wa.y * g[0], wa.y * g[1], wa.y * g[2], wa.y * g[3]);
+                        if (wa.z != 0.f) red_add_f32x4(gvimg + off.z, wa.z * g[0], wa.z * g[1], wa.z * g[2], wa.z * g[3]);
+                        if (wa.w != 0.f) red_add_f32x4(gvimg + off.w, wa.w * g[0], wa.w * g[1], wa.w * g[2], wa.w * g[3]);
+                    }
+                }
+                group_reduce_scatter<G, 4 * GH>(t, gl);
+                th[h][0] = t[0];
+                th[h][1] = t[1];
+            }
+            __syncwarp();
+
+            float t[4];
+            {
+                const int src = (lane & ~(G - 1)) | (2 * (gl % GH));
+                const bool second = gl >= GH;
+                const float a0 = __shfl_sync(kFullMask, th[0][0], src), a1 = __shfl_sync(kFullMask, th[0][1], src);
+                const float a2 = __shfl_sync(kFullMask, th[0][0], src + 1), a3 = __shfl_sync(kFullMask, th[0][1], src + 1);
+                const float b0_ = __shfl_sync(kFullMask, th[1][0], src), b1 = __shfl_sync(kFullMask, th[1][1], src);
+                const float b2 = __shfl_sync(kFullMask, th[1][0], src + 1), b3 = __shfl_sync(kFullMask, th[1][1], src + 1);
+                t[0] = second ? b0_ : a0; t[1] = second ? b1 : a1; t[2] = second ? b2 : a2; t[3] = second ? b3 : a3;
+            }
+            if (has) {
+                float gx = 0.f, gy = 0.f, ga = 0.f;
+                if (gm.live) {
+                    const float t00 = (gm.vmask & 1u) ? t[0] : 0.f, t01 = (gm.vmask & 2u) ? t[1] : 0.f;
+                    const float t10 = (gm.vmask & 4u) ? t[2] : 0.f, t11 = (gm.vmask & 8u) ? t[3] : 0.f;
+                    ga = gm.w00 * t00 + gm.w01 * t01 + gm.w10 * t10 + gm.w11 * t11;
+                    gx = gm.Wf * gm.a * (gm.hy * (t01 - t00) + gm.ly * (t11 - t10));
+                    gy = gm.Hf * gm.a * (gm.hx * (t10 - t00) + gm.lx * (t11 - t01));
+                }
+                const long si = qm * LP + sidx;
+                if constexpr (FUSED) {
+                    const float ox = gm.live ? __fdiv_rn(gx, gm.Wf) : 0.f, oy = gm.live ? __fdiv_rn(gy, gm.Hf) : 0.f;
+                    __stcs(reinterpret_cast<float2 *>(grad_loc + 2 * si), make_float2(ox, oy));
+                    pa[0] = pa[1]; pa[1] = pa[2]; pa[2] = pa[3]; pa[3] = a_cur;
+                    pg[0] = pg[1]; pg[1] = pg[2]; pg[2] = pg[3]; pg[3] = ga;
+                } else {
+                    __stcs(reinterpret_cast<float2 *>(grad_loc + 2 * si), make_float2(gx, gy));
+                    __stcs(grad_attn + si, ga);
+                }
+            } else if constexpr (FUSED) {
+                pa[0] = pa[1]; pa[1] = pa[2]; pa[2] = pa[3]; pa[3] = 0.f;
+                pg[0] = pg[1]; pg[1] = pg[2]; pg[2] = pg[3]; pg[3] = 0.f;
+            }
+        }
+        if constexpr (FUSED) {
+            float dot = 0.f;
+#pragma unroll
+            for (int b = 0; b < kMaxBatches; ++b) dot += pa[b] * pg[b];
+            dot = group_allreduce_sum<G>(dot);
+            const int nb = (LP + G - 1) / G;
+#pragma unroll
+            for (int b = 0; b < kMaxBatches; ++b) {
+                const int sidx = (b - (kMaxBatches - nb)) * G + gl;
+                if (b >= kMaxBatches - nb && qvalid && sidx < LP) grad_attn[qm * LP + sidx] = pa[b] * (pg[b] - dot);
+            }
+        }
+    }
+
+    const int nbs = s_plan.nbs;
+    if (nbs == 0) return;                                // block-uniform: nothing was binned
+    __syncthreads();
+
+    // ---- phase B: histogram -> exclusive offsets (in place), then the counting-sort permutation --------
+    unsigned short *hh = reinterpret_cast<unsigned short *>(s_hist);
+    {
+        constexpr int BPT = (C::HIST_HALVES + kBinThreads - 1) / kBinThreads;
+        int c[BPT], sum = 0;
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const int idx = tid * BPT + i;
+            c[i] = idx < C::HIST_HALVES ? hh[idx] : 0;
+            sum += c[i];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(kFullMask, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl;
+        __syncthreads();
+        int base = incl - sum;
+        for (int w2 = 0; w2 < warp; ++w2) base += s_warp_tot[w2];
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const int idx = tid * BPT + i;
+            if (idx < C::HIST_HALVES) hh[idx] = (unsigned short)base;
+            base += c[i];
+        }
+    }
+    __syncthreads();
+    unsigned short *s_idx = reinterpret_cast<unsigned short *>(s_rec);    // phase A is over: reuse the record area
+    {
+        const int nq = min(QC, d.Lq - q0);
+        for (int e = tid; e < nq * kBinSamples; e += kBinThreads) {
+            if ((e & (kBinSamples - 1)) >= nbs) continue;
+            const unsigned pk = s_ent[e].w;
+            if (pk != kNoEntry) s_idx[hh[pk & 0xffffu] + (pk >> 16)] = (unsigned short)e;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: one lane group per non-empty base-corner cell ------------------------------------
+    // Every sample of the cell shares its four corner pixels: the group reads each sample's grad_out row
+    // ONCE (a pixel-owner formulation reads it four times -- measured: more L1 data-pipe wavefronts than the
+    // reductions it replaces), forms the four corner rows in registers and sends one REDG line per corner.
+    const unsigned gmask = (G == 32) ? kFullMask : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const int nbins = s_plan.nbins, lb = s_plan.lb;
+    const float *gq = s_g + gl * kChannelsPerLane;
+    for (;;) {
+        int c = 0;
+        if (gl == 0) c = atomicAdd(&s_next, 1);
+        c = __shfl_sync(gmask, c, 0, G);
+        if (c >= nbins) break;
+        const int i0 = hh[c], i1 = hh[c + 1];
+        if (i0 == i1) continue;
+        int l = lb;
+        while (l < d.L - 1 && c < s_plan.binbase[l]) ++l;            // binbase grows towards the finer levels
+        const LevelInfo li = s_lv[l];
+        const int cc = c - s_plan.binbase[l];
+        const int by = cc / (li.W + 1), bx = cc - by * (li.W + 1);
+        const int y0 = by - 1, x0 = bx - 1;
+        float a00[4] = {0.f, 0.f, 0.f, 0.f}, a01[4] = {0.f, 0.f, 0.f, 0.f};
+        float a10[4] = {0.f, 0.f, 0.f, 0.f}, a11[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int i = i0; i < i1; ++i) {
+            const int e = s_idx[i];
+            const uint4 en = s_ent[e];
+            const float4 gg = *reinterpret_cast<const float4 *>(gq + (e / kBinSamples) * D);
+            const float a = __uint_as_float(en.x), lx = __uint_as_float(en.y), ly = __uint_as_float(en.z);
+            const float hy = 1.f - ly, hx = 1.f - lx;
+            const float w00 = (hy * hx) * a, w01 = (hy * lx) * a, w10 = (ly * hx) * a, w11 = (ly * lx) * a;
+            a00[0] += w00 * gg.x; a00[1] += w00 * gg.y; a00[2] += w00 * gg.z; a00[3] += w00 * gg.w;
+            a01[0] += w01 * gg.x; a01[1] += w01 * gg.y; a01[2] += w01 * gg.z; a01[3] += w01 * gg.w;
+            a10[0] += w10 * gg.x; a10[1] += w10 * gg.y; a10[2] += w10 * gg.z; a10[3] += w10 * gg.w;
+            a11[0] += w11 * gg.x; a11[1] += w11 * gg.y; a11[2] += w11 * gg.z; a11[3] += w11 * gg.w;
+        }
+        // corners outside the map receive nothing (zero padding, ms_deform_im2col_cuda.cuh:125-152)
+        const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= li.H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= li.W - 1;
+        float *row = gvimg + (li.start + y0 * li.W + x0) * xs;
+        const int ys = li.W * xs;
+        if (y0ok && x0ok) red_add_f32x4(row, a00[0], a00[1], a00[2], a00[3]);
+        if (y0ok && x1ok) red_add_f32x4(row + xs, a01[0], a01[1], a01[2], a01[3]);
+        if (y1ok && x0ok) red_add_f32x4(row + ys, a10[0], a10[1], a10[2], a10[3]);
+        if (y1ok && x1ok) red_add_f32x4(row + ys + xs, a11[0], a11[1], a11[2], a11[3]);
+    }
+}
+
+template <typename VT, int D, bool FUSED>
+int run_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
+            const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, cudaStream_t st)
+{
+    using C = BinCfg<D>;
+    auto kern = bwd_bin_kernel<VT, D, FUSED>;
+    static bool prepared[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64 || !prepared[dev]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) prepared[dev] = true;
+    }
+    const long n_chunks = (d.Lq + C::QC - 1) / C::QC;
+    const long grid = (long)d.N * d.M * n_chunks;
+    if (grid > 0x7fffffffL) return kUnsupported;
+    kern<<<(unsigned)grid, kBinThreads, C::SMEM, st>>>((const VT *)value, shapes, lsi, (const float *)loc,
+                                                        (const float *)attn, (const VT *)grad_out, (float *)gv,
+                                                        (float *)gl, (float *)ga, d, (const float *)ref,
+                                                        min(kBinSamples, tuning().bwd_pipe > 0 ? tuning().bwd_pipe : kBinSamples));
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+template <typename VT, bool FUSED>
+int dispatch_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
+                 const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, cudaStream_t st)
+{
+    switch (d.D) {
+    case 16: return run_bin<VT, 16, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+    case 32: return run_bin<VT, 32, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+    case 64: return run_bin<VT, 64, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+    }
+    return kUnsupported;
+}
+
+}  // namespace
+
+// bwd_variant: -1 default (binned kernel for long query sets); 20 force it for any Lq; 10/11/99 never.
+bool binned_backward_applies(const Dims &d, DType dt, bool vec_ok)
+{
+    const int v = tuning().bwd_variant;
+    if (!vec_ok || dt == DType::F64 || !(d.D == 16 || d.D == 32 || d.D == 64)) return false;
+    if ((long)d.S * d.M * d.D >= (1L << 31) || d.L * d.P < 1) return false;
+    if (v == 20) return true;
+    return v == -1 && d.Lq >= kBinMinQueries;
+}
+
+// grad_value must already be zero-filled.  `ref` != nullptr selects the fused pre-processing flavour
+// (loc = raw offsets, attn = raw logits).
+int launch_backward_binned(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                           const void *attn, const void *grad_out, void *gv, void *gl, void *ga, const Dims &d,
+                           const void *ref, cudaStream_t st)
+{
+    if (ref) {
+        if (dt == DType::F32) return dispatch_bin<float, true>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+        return dispatch_bin<__nv_bfloat16, true>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+    }
+    if (dt == DType::F32) return dispatch_bin<float, false>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, nullptr, st);
+    return dispatch_bin<__nv_bfloat16, false>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, nullptr, st);
+}
+
+}  // namespace msda

@@ -198,6 +198,11 @@ int launch_forward_fused(DType dt, const void *value, const int64_t *shapes, con
 int launch_backward_fused(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref,
                           const void *offsets, const void *logits, const void *grad_out, void *grad_value,
                           void *grad_offsets, void *grad_logits, const Dims &d, cudaStream_t st);
+// msda_backward_binned.cu: coarse levels combined in shared memory (long query sets); grad_value pre-zeroed
+bool binned_backward_applies(const Dims &d, DType dt, bool vec_ok);
+int launch_backward_binned(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                           const void *attn, const void *grad_out, void *grad_value, void *grad_loc, void *grad_attn,
+                           const Dims &d, const void *ref, cudaStream_t st);
 const char *forward_kernel_name(DType dt, int D, int L, int P, bool vec_ok);
 const char *backward_kernel_name(DType dt, int D, int L, int P, bool vec_ok);
 

@@ -124,6 +124,7 @@ struct SampleGeom {
     float a;                    // attention weight
     float Wf, Hf;
     unsigned vmask;             // bit0..3: corner 00, 01, 10, 11 lies inside the map
+    int cell;                   // (y0+1)*(W+1) + (x0+1): the sample's base-corner cell on the (H+1)x(W+1) lattice
     bool live;                  // sample exists (index < L*P, query valid) and is inside the window
 };
 
@@ -223,7 +224,7 @@ __device__ __forceinline__ SampleGeom build_record(uint32_t *rec_off, uint32_t *
     gm.live = false;
     gm.w00 = gm.w01 = gm.w10 = gm.w11 = 0.f;
     gm.hy = gm.ly = gm.hx = gm.lx = 0.f;
-    gm.a = 0.f; gm.Wf = 0.f; gm.Hf = 0.f; gm.vmask = 0u;
+    gm.a = 0.f; gm.Wf = 0.f; gm.Hf = 0.f; gm.vmask = 0u; gm.cell = 0;
     int4 off = make_int4(0, 0, 0, 0);
     float4 wa = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has) {
@@ -243,6 +244,7 @@ __device__ __forceinline__ SampleGeom build_record(uint32_t *rec_off, uint32_t *
             gm.vmask = (y0ok && x0ok ? 1u : 0u) | (y0ok && x1ok ? 2u : 0u) | (y1ok && x0ok ? 4u : 0u) |
                        (y1ok && x1ok ? 8u : 0u);
             gm.live = true;
+            gm.cell = (t.y0 + 1) * (li.W + 1) + t.x0 + 1;
             const int r0 = (li.start + y0c * li.W) * xs, r1 = (li.start + y1c * li.W) * xs;
             off = make_int4(r0 + x0c * xs, r0 + x1c * xs, r1 + x0c * xs, r1 + x1c * xs);
             wa = make_float4(gm.w00 * a, gm.w01 * a, gm.w10 * a, gm.w11 * a);

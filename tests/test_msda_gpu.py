@@ -251,6 +251,62 @@ def test_generic_and_record_kernels_agree(msda):
         assert O.rel_l2(x, y) < tol
 
 
+# --- binned backward (msda_backward_binned.cu): coarse levels combined in shared memory ---------------
+# bwd_variant 20 forces the kernel for any Lq (by default it serves Lq >= 1024); which levels are binned is
+# decided on the device: coarsest first while cells fit 704, samples per query fit 8 and H*W <= QC*P.
+BIN_CASES = [
+    # (shapes, N, M, D, Lq, P)
+    ([(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 300, 4),    # pyramid: levels 2 and 3 binned (8 samples); two chunks, ragged
+    ([(6, 4), (3, 2)], 1, 2, 32, 2, 2),                          # ops/test.py shape: every level binned
+    ([(9, 7), (5, 4), (3, 3)], 2, 4, 32, 519, 3),                # P = 3: two levels (6 samples), three chunks
+    ([(9, 7), (5, 4)], 2, 4, 16, 700, 8),                        # D = 16 (4-lane groups), P = 8: one level binned
+    ([(9, 7), (5, 4)], 2, 4, 64, 150, 4),                        # D = 64 (16-lane groups, 128-query chunks)
+    ([(16, 16)], 1, 1, 32, 257, 4),                              # single level, 289 cells, one query in the last chunk
+    ([(40, 40), (30, 30)], 1, 2, 32, 300, 4),                    # no level fits the cell budget: direct reductions only
+    ([(9, 7), (5, 4)], 2, 4, 32, 100, 16),                       # P = 16 exceeds the 8 entry slots: nothing binned
+    ([(9, 7), (1, 1)], 2, 3, 32, 260, 4),                        # 1x1 coarsest level: four cells, one hot row
+    ([(20, 25), (2, 2)], 1, 2, 32, 300, 4),                      # fine level too large for 704 cells -> only the 2x2 level
+]
+
+
+@pytest.mark.parametrize("case", BIN_CASES, ids=lambda c: f"M{c[2]}D{c[3]}Lq{c[4]}P{c[5]}L{len(c[0])}")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_binned_backward_vs_oracle_and_direct(msda, case, dtype):
+    """the binned kernel against the fp64 oracle, and against the record kernel: grad_loc / grad_attn come from
+    identical arithmetic (bitwise equal), grad_value differs only in summation order."""
+    shapes, N, M, D, Lq, P = case
+    value, sh, lsi, loc, attn, grad_out = _random_case(300 + D + Lq, shapes, N, M, D, Lq, P, spread=1.4, shift=-0.2)
+    L = msda._lib
+    ct = torch.float32
+    try:
+        L.set_tuning("bwd_variant", 20)
+        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=f"binned {case}")
+        b = run_ours(msda, value.to(dtype), sh, lsi, loc.to(ct), attn.to(ct), grad_out.to(dtype))
+        L.set_tuning("bwd_variant", 11)
+        a = run_ours(msda, value.to(dtype), sh, lsi, loc.to(ct), attn.to(ct), grad_out.to(dtype))
+    finally:
+        L.set_tuning("bwd_variant", -1)
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert O.rel_l2(b[1], a[1]) < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
+def test_binned_backward_is_the_default_for_long_query_sets(msda, cuda_device):
+    """Lq >= 1024 takes the binned kernel without any tuning; hot coarse pixels (every query samples the same
+    corner of the coarsest level) stress the per-cell counters: 2048 entries in one cell."""
+    shapes, N, M, D, Lq, P = [(12, 40), (6, 20), (3, 10), (2, 5)], 1, 2, 32, 1100, 4
+    value, sh, lsi, loc, attn, grad_out = _random_case(41, shapes, N, M, D, Lq, P, spread=1.2, shift=-0.1)
+    loc[:, :, :, 2:, :, :] = 0.26                                 # all coarse samples in one cell
+    check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.float32, label="hot cell")
+    L = msda._lib
+    a = run_ours(msda, value.float(), sh, lsi, loc.float(), attn.float(), grad_out.float())
+    try:
+        L.set_tuning("bwd_variant", 11)
+        b = run_ours(msda, value.float(), sh, lsi, loc.float(), attn.float(), grad_out.float())
+    finally:
+        L.set_tuning("bwd_variant", -1)
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and O.rel_l2(a[1], b[1]) < 1e-5
+
+
 def test_edge_locations_exact_borders(msda):
     g = load_golden("op", "d32_edges")
     for dtype in (torch.float64, torch.float32):
@@ -479,7 +535,16 @@ def test_c_abi_direct_call_and_error_codes(msda, cuda_device):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
 @pytest.mark.parametrize("shape", [([(5, 7), (3, 4), (1, 1)], 2, 8, 32, 37, 4), ([(4, 3)], 1, 3, 16, 9, 2), ([(6, 5), (2, 2)], 1, 2, 24, 5, 3)])
-def test_guard_bands_no_out_of_bounds_access(msda, cuda_device, dtype, shape):
+@pytest.mark.parametrize("bwd_variant", [-1, 20])
+def test_guard_bands_no_out_of_bounds_access(msda, cuda_device, dtype, shape, bwd_variant):
+    msda._lib.set_tuning("bwd_variant", bwd_variant)
+    try:
+        _guard_bands(msda, cuda_device, dtype, shape)
+    finally:
+        msda._lib.set_tuning("bwd_variant", -1)
+
+
+def _guard_bands(msda, cuda_device, dtype, shape):
     """compute-sanitizer is closed on this GPU pool, so bounds are checked the hard way: every tensor
     is carved out of a larger buffer whose surroundings are NaN (inputs) or a sentinel (outputs), the
     locations hammer the borders, and the kernels are called through the raw C ABI.  An out-of-range
@@ -592,7 +657,17 @@ FUSED_CASES = [
 
 @pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: f"M{c[2]}D{c[3]}Lq{c[4]}P{c[5]}L{len(c[0])}")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_fused_preprocessing_matches_unfused_and_oracle(msda, cuda_device, case, dtype):
+@pytest.mark.parametrize("bwd_variant", [-1, 20])
+def test_fused_preprocessing_matches_unfused_and_oracle(msda, cuda_device, case, dtype, bwd_variant):
+    """bwd_variant 20: the fused flavour of the binned backward (default for Lq >= 1024)"""
+    msda._lib.set_tuning("bwd_variant", bwd_variant)
+    try:
+        _fused_vs_unfused(msda, cuda_device, case, dtype)
+    finally:
+        msda._lib.set_tuning("bwd_variant", -1)
+
+
+def _fused_vs_unfused(msda, cuda_device, case, dtype):
     from monosowa_b200.ops.functions import MSDeformAttnFusedFunction, fused_supported
     shapes, N, M, D, Lq, P = case
     dev = cuda_device

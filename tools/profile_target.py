@@ -15,8 +15,12 @@ ap.add_argument("--dtype", default="f32")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--mode", default="model")
 ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--set", default="", help="comma-separated key=value for msda_set_tuning")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
+for kv in filter(None, a.set.split(",")):
+    k_, v_ = kv.split("=")
+    msda._lib.set_tuning(k_, int(v_))
 wl = W.config(1, batch=a.batch, loc_mode=a.mode, dtype={"f32": torch.float32, "bf16": torch.bfloat16}[a.dtype])
 d = W.make_inputs(wl, device=dev)
 a5 = (d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"])
