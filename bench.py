@@ -291,21 +291,60 @@ def run_ours(args, wl):
         cur.wait_stream(s_out)
         cur.wait_stream(s_in)
 
-    for _ in range(max(1, min(args.warmup, 3))):
-        step_e2e()
-    barrier()
-    e2e_steps = max(1, min(args.steps, 10))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        step_e2e()
-    e1.record()
-    barrier()
-    d2h_bytes = sum(t.numel() * t.element_size() for t in host_out)
-    e2e_ms = e0.elapsed_time(e1) / e2e_steps
-    e2e_value, e2e_ms_max = aggregate(ab["total"], e2e_ms, world, reduce_fn if use_dist else None)
-    # sanity: the e2e path produced the same forward as the device path
+    def time_e2e(step_fn):
+        for _ in range(max(1, min(args.warmup, 3))):
+            step_fn()
+        barrier()
+        n_ = max(1, min(args.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_):
+            step_fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / n_
+
+    # (a) the host-buffer entry point of the C ABI (msda_host_step_f32): one call per step, the library
+    #     pipelines the batch image by image on its own copy streams
+    go_host = host_in["grad_out"].view(wl.batch, -1, wl.heads * wl.head_dim)
+
+    def step_host():
+        msda.host_step(host_in["value"], d["shapes"], d["lsi"], host_in["loc"], host_in["attn"], go_host,
+                       images_per_chunk=args.e2e_images_per_chunk, results=tuple(host_out), synchronize=False)
+
+    e2e_ms = time_e2e(step_host)
     chk = torch.equal(host_out[0].to(dev), out) if rank == 0 else True
+    # (b) the same through MSDeformAttnFunction.apply + autograd with a Python-level 3-stream pipeline
+    e2e_autograd_ms = time_e2e(step_e2e)
+    d2h_bytes = sum(t.numel() * t.element_size() for t in host_out)
+
+    # PCIe copy rates of this box (the e2e leg's own roofline): the same pinned buffers, one direction at a
+    # time and both at once; lower bound of an e2e step = max(h2d_bytes / h2d rate, d2h_bytes / d2h rate), duplex
+    def copy_rate(h2d, d2h, reps=3):
+        res = (out, grads[0], grads[1], grads[2])
+        best = float("inf")
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if h2d:
+                with torch.cuda.stream(s_in):
+                    for k in host_in:
+                        dev_in[k].copy_(host_in[k], non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s_out):
+                    for h, t in zip(host_out, res):
+                        h.copy_(t, non_blocking=True)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        return best
+    pcie = None
+    if world == 1:
+        t_h, t_d, t_b = copy_rate(True, False), copy_rate(False, True), copy_rate(True, True)
+        pcie = {"h2d_GBps": h2d_bytes / t_h / 1e9, "d2h_GBps": d2h_bytes / t_d / 1e9,
+                "duplex_ms": t_b * 1e3, "note": "full-duplex copy of one step's inputs and results, no kernels: "
+                                                "the floor of an e2e step on this box"}
+    e2e_value, e2e_ms_max = aggregate(ab["total"], e2e_ms, world, reduce_fn if use_dist else None)
+    chk = chk and (torch.equal(host_out[0].to(dev), out) if rank == 0 else True)   # both e2e paths reproduce the device forward
 
     if rank != 0:
         if use_dist:
@@ -325,14 +364,17 @@ def run_ours(args, wl):
         "fwd_GBps": ab["fwd"] / (fwd_ms * 1e-3) / 1e9, "bwd_GBps": ab["bwd"] / (bwd_ms * 1e-3) / 1e9,
         "algorithmic_bytes": {"fwd": ab["fwd"], "bwd": ab["bwd"], "gather_cache_level": ab["gather"]},
         "kernels": {"fwd": msda._lib.lib.msda_describe_forward(32, 0, wl.head_dim, wl.L, wl.points).decode(),
-                    "bwd": msda._lib.lib.msda_describe_backward(32, 0, wl.head_dim, wl.L, wl.points).decode()},
+                    "bwd": msda._lib.lib.msda_describe_backward_lq(32, 0, wl.head_dim, wl.L, wl.points, wl.Lq).decode()},
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": load_traffic(dom[0]), "peak_source": peak_src,
                      "note": "achieved = algorithmic bytes of the launch / CUDA-event time on the launch stream; "
                              "bwd includes its cudaMemsetAsync of grad_value"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_max, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "chunks": chunks, "matches_device_path": bool(chk),
-                "api": "MSDeformAttnFunction.apply + autograd, pinned host buffers, 3-stream pipeline"},
+                "d2h_bytes_per_step": d2h_bytes, "chunks": chunks, "matches_device_path": bool(chk), "pcie": pcie,
+                "api": "msda_host_step_f32 (C ABI, pinned host buffers in and out; monosowa_b200.host_step), "
+                       f"{args.e2e_images_per_chunk} image(s) per pipeline chunk",
+                "autograd_api_ms_per_step": e2e_autograd_ms,
+                "autograd_api": f"MSDeformAttnFunction.apply + autograd, Python 3-stream pipeline, {chunks} chunks"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "lib": msda._lib.build_info(),
@@ -393,6 +435,7 @@ def main():
     ap.add_argument("--loc-mode", default="model", choices=["model", "uniform"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-images-per-chunk", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")

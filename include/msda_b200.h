@@ -44,6 +44,7 @@
 #ifndef MSDA_B200_H_
 #define MSDA_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -132,6 +133,34 @@ int msda_backward_fused_bf16(const void *value, const int64_t *spatial_shapes,
                              void *grad_logits, int N, int S, int M, int D, int L, int Lq, int P,
                              void *stream);
 
+/* ---- host-buffer step --------------------------------------------------------------------------
+ * One forward + backward of a whole batch whose tensors live in HOST memory (pinned memory for
+ * asynchronous copies): value / sampling_loc / attn_weight / grad_out in, out / grad_value /
+ * grad_loc / grad_attn back, all with the layouts above (grad_value is fp32 for the bf16 flavour, as
+ * in msda_backward_bf16).  spatial_shapes and level_start_index stay DEVICE pointers.  The reference
+ * has no counterpart: its extension takes CUDA tensors only (ops/src/ms_deform_attn.h:29-38), so a
+ * caller with host data pays cudaMemcpy + kernels + cudaMemcpy serially.  Here the batch is pipelined
+ * in chunks of `images_per_chunk` images (images are independent, cuh:269) over two internal copy
+ * streams and `stream`: H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap.
+ *   workspace : DEVICE scratch of at least msda_host_step_workspace_bytes(...) bytes, 256-byte
+ *               aligned, owned by the caller (the library never allocates device memory).
+ * Nothing blocks the host; results are valid once `stream` has been synchronised.  Calls on one
+ * device are serialised by a mutex (they share the copy streams). */
+int msda_host_step_f32(const void *h_value, const int64_t *spatial_shapes,
+                       const int64_t *level_start_index, const void *h_sampling_loc,
+                       const void *h_attn_weight, const void *h_grad_out, void *h_out,
+                       void *h_grad_value, void *h_grad_loc, void *h_grad_attn, void *workspace,
+                       size_t workspace_bytes, int N, int S, int M, int D, int L, int Lq, int P,
+                       int images_per_chunk, void *stream);
+int msda_host_step_bf16(const void *h_value, const int64_t *spatial_shapes,
+                        const int64_t *level_start_index, const void *h_sampling_loc,
+                        const void *h_attn_weight, const void *h_grad_out, void *h_out,
+                        void *h_grad_value_f32, void *h_grad_loc, void *h_grad_attn, void *workspace,
+                        size_t workspace_bytes, int N, int S, int M, int D, int L, int Lq, int P,
+                        int images_per_chunk, void *stream);
+size_t msda_host_step_workspace_bytes(int is_bf16, int S, int M, int D, int L, int Lq, int P,
+                                      int images_per_chunk);
+
 /* ---- introspection ---------------------------------------------------------------------- */
 int msda_abi_version(void);            /* == MSDA_ABI_VERSION                                */
 const char *msda_build_info(void);     /* "sm_100a nvcc <ver> <date>"                        */
@@ -140,7 +169,7 @@ long long msda_launch_count(void);     /* kernels this library has launched so f
 
 /* Kernel-selection knobs, for benchmarking A/B runs only (process-wide, not thread-safe
  * against concurrent launches).  Keys: "fwd_variant" / "bwd_variant" (10, 11 = record kernel with
- * work order 0 / 1, 99 = generic kernels), "fwd_pipe" / "bwd_pipe" (register-cap / loop flavour of
+ * work order 0 / 1, 20 = binned backward for any Lq, 99 = generic kernels), "fwd_pipe" / "bwd_pipe" (register-cap / loop flavour of
  * the record kernels, see the launch code).  value -1 restores the measured default.
  * Returns MSDA_OK or MSDA_ERR_BAD_SHAPE (unknown key). */
 int msda_set_tuning(const char *key, int value);
@@ -150,6 +179,9 @@ int msda_get_tuning(const char *key);
  * "bwd_rec_bf16", "fwd_generic_f64", ... (static storage; for logs, tests and bench.py). */
 const char *msda_describe_forward(int dtype_bits, int is_bf16, int D, int L, int P);
 const char *msda_describe_backward(int dtype_bits, int is_bf16, int D, int L, int P);
+/* The backward choice also depends on the number of queries: long query sets (Lq >= 1024) take the
+ * binned kernel ("bwd_bin_f32" / "bwd_bin_bf16": coarse-level grad_value combined in shared memory). */
+const char *msda_describe_backward_lq(int dtype_bits, int is_bf16, int D, int L, int P, int Lq);
 
 #ifdef __cplusplus
 }

@@ -17,11 +17,15 @@ _BWD = [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]
 _FFWD = [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]
 _FBWD = [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]
 
+_HOST = [_vp] * 11 + [ctypes.c_size_t] + [_int] * 8 + [_vp]
+
 EXPORTS = {
     "msda_forward_f32": (_int, _FWD), "msda_forward_f64": (_int, _FWD), "msda_forward_bf16": (_int, _FWD),
     "msda_backward_f32": (_int, _BWD), "msda_backward_f64": (_int, _BWD), "msda_backward_bf16": (_int, _BWD),
     "msda_forward_fused_f32": (_int, _FFWD), "msda_forward_fused_bf16": (_int, _FFWD),
     "msda_backward_fused_f32": (_int, _FBWD), "msda_backward_fused_bf16": (_int, _FBWD),
+    "msda_host_step_f32": (_int, _HOST), "msda_host_step_bf16": (_int, _HOST),
+    "msda_host_step_workspace_bytes": (ctypes.c_size_t, [_int] * 8),
     "msda_abi_version": (_int, []),
     "msda_build_info": (ctypes.c_char_p, []),
     "msda_last_error": (ctypes.c_char_p, []),
@@ -30,27 +34,44 @@ EXPORTS = {
     "msda_get_tuning": (_int, [ctypes.c_char_p]),
     "msda_describe_forward": (ctypes.c_char_p, [_int] * 5),
     "msda_describe_backward": (ctypes.c_char_p, [_int] * 5),
+    "msda_describe_backward_lq": (ctypes.c_char_p, [_int] * 6),
 }
 ABI_VERSION = 1
 ERR_UNSUPPORTED = -4
 
 
+def _bind(lib: ctypes.CDLL) -> ctypes.CDLL:
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)          # AttributeError here = ABI mismatch
+        fn.restype, fn.argtypes = res, args
+    if lib.msda_abi_version() != ABI_VERSION:
+        raise AttributeError(f"ABI version {lib.msda_abi_version()} != expected {ABI_VERSION}")
+    return lib
+
+
 def _open() -> ctypes.CDLL:
+    from . import build as _build
     if not os.path.exists(LIB_PATH):
         try:
-            from . import build as _build
             _build.build()
         except Exception as exc:  # noqa: BLE001
             raise ImportError(
                 f"monosowa_b200: {LIB_PATH} is missing and could not be built ({exc}). "
-                "Run `python -m monosowa_b200.build`. There is no CPU or PyTorch fallback.") from exc
+                "Run `python monosowa_b200/build.py`. There is no CPU or PyTorch fallback.") from exc
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (res, args) in EXPORTS.items():
-        fn = getattr(lib, name)          # AttributeError here = ABI mismatch: fail loudly
-        fn.restype, fn.argtypes = res, args
-    if lib.msda_abi_version() != ABI_VERSION:
-        raise ImportError(f"monosowa_b200: ABI version {lib.msda_abi_version()} != expected {ABI_VERSION}; rebuild")
-    return lib
+    try:
+        return _bind(lib)
+    except AttributeError as stale:
+        # a library left over from an older source tree (a symbol of include/msda_b200.h is missing):
+        # rebuild once from the sources next to it, then fail loudly if it still does not match
+        import _ctypes
+        _ctypes.dlclose(lib._handle)
+        try:
+            _build.build(force=True)
+            return _bind(ctypes.CDLL(LIB_PATH))
+        except Exception as exc:  # noqa: BLE001
+            raise ImportError(f"monosowa_b200: {LIB_PATH} does not match include/msda_b200.h ({stale}) and the "
+                              f"rebuild failed ({exc}). There is no CPU or PyTorch fallback.") from exc
 
 
 lib = _open()

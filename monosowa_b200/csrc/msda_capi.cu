@@ -3,6 +3,7 @@
 // (MonoDETR/lib/models/monodetr/ops/src/cuda/ms_deform_attn_cuda.cu:28-52, 93-119) as far as a
 // raw-pointer interface can (contiguity / device placement are the Python layer's job).
 #include <atomic>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -132,6 +133,139 @@ static int fused_impl(const char *fn, DType dt, bool backward, const void *value
     return cuda_result(rc, fn);
 }
 
+// ---- host-buffer step ------------------------------------------------------------------------------
+// forward + backward of a batch whose tensors live in HOST memory (include/msda_b200.h, "host-buffer
+// step").  Images are independent (the value index is prefixed by n, reference cuh:269), so the batch is
+// pipelined in chunks of whole images over two internal copy streams and the caller's stream:
+//   s_in : H2D of chunk i+1     |  stream : forward + backward of chunk i  |  s_out : D2H of chunk i-1
+// through a ring of kHostStages device stages carved from the caller's workspace.  Nothing here blocks
+// the host; the caller synchronises `stream` before reading the results.
+constexpr int kHostStages = 3;
+
+struct HostPipe {
+    bool ready = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t start = nullptr, done = nullptr, in[kHostStages] = {}, cmp[kHostStages] = {}, out[kHostStages] = {};
+};
+static HostPipe g_pipe[64];
+static std::mutex g_pipe_mu;
+
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+struct HostStage {
+    size_t value, loc, attn, grad_out, out, gv, gl, ga, total;
+};
+
+static HostStage host_stage_layout(DType dt, const Dims &d, int images)
+{
+    const size_t ve = dt == DType::F64 ? 8 : (dt == DType::F32 ? 4 : 2), ce = dt == DType::F64 ? 8 : 4;
+    const size_t n = (size_t)images;
+    const size_t vb = n * d.S * d.M * d.D * ve, lb = n * d.Lq * d.M * d.L * d.P * 2 * ce, ab = lb / 2;
+    const size_t ob = n * d.Lq * d.M * d.D * ve, gvb = n * d.S * d.M * d.D * ce;
+    HostStage st;
+    size_t o = 0;
+    st.value = o; o += align256(vb);
+    st.loc = o; o += align256(lb);
+    st.attn = o; o += align256(ab);
+    st.grad_out = o; o += align256(ob);
+    st.out = o; o += align256(ob);
+    st.gv = o; o += align256(gvb);
+    st.gl = o; o += align256(lb);
+    st.ga = o; o += align256(ab);
+    st.total = o;
+    return st;
+}
+
+static int host_pipe(HostPipe **out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    HostPipe &p = g_pipe[dev];
+    if (!p.ready) {
+        if ((e = cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        cudaEvent_t *evs[] = {&p.start, &p.done};
+        for (cudaEvent_t *ev : evs)
+            if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+        for (int i = 0; i < kHostStages; ++i) {
+            if ((e = cudaEventCreateWithFlags(&p.in[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+            if ((e = cudaEventCreateWithFlags(&p.cmp[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+            if ((e = cudaEventCreateWithFlags(&p.out[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+        }
+        p.ready = true;
+    }
+    *out = &p;
+    return 0;
+}
+
+#define MSDA_CU(call)                                           \
+    do {                                                        \
+        cudaError_t e_ = (call);                                \
+        if (e_ != cudaSuccess) return cuda_result((int)e_, fn); \
+    } while (0)
+
+static int host_step_impl(const char *fn, DType dt, const void *h_value, const int64_t *shapes, const int64_t *lsi,
+                          const void *h_loc, const void *h_attn, const void *h_grad_out, void *h_out, void *h_gv,
+                          void *h_gl, void *h_ga, void *workspace, size_t workspace_bytes, int N, int S, int M, int D,
+                          int L, int Lq, int P, int images_per_chunk, void *stream)
+{
+    Checked c;
+    if (int rc = check_common(fn, dt, h_value, shapes, lsi, h_loc, h_attn, N, S, M, D, L, Lq, P, &c)) return rc;
+    if (images_per_chunk < 1) return fail(MSDA_ERR_BAD_SHAPE, "%s: images_per_chunk must be >= 1", fn);
+    if (N == 0) return cuda_result(0, fn);
+    if (!h_grad_out || !h_out || !h_gv || !h_gl || !h_ga || !workspace)
+        return fail(MSDA_ERR_NULL_POINTER, "%s: a host result pointer, grad_out or the workspace is NULL", fn);
+    const int cb = images_per_chunk < N ? images_per_chunk : N;
+    const HostStage lay = host_stage_layout(dt, c.d, cb);
+    if (workspace_bytes < (size_t)kHostStages * lay.total || !aligned(workspace, 256))
+        return fail(MSDA_ERR_BAD_SHAPE, "%s: workspace too small or not 256-byte aligned (%zu bytes needed)", fn,
+                    (size_t)kHostStages * lay.total);
+    std::lock_guard<std::mutex> lock(g_pipe_mu);
+    HostPipe *p = nullptr;
+    if (int rc = host_pipe(&p)) return cuda_result(rc, fn);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ve = dt == DType::F64 ? 8 : (dt == DType::F32 ? 4 : 2), ce = dt == DType::F64 ? 8 : 4;
+    const size_t vb = (size_t)S * M * D * ve, lb = (size_t)Lq * M * L * P * 2 * ce, ab = lb / 2;
+    const size_t ob = (size_t)Lq * M * D * ve, gvb = (size_t)S * M * D * ce;
+
+    MSDA_CU(cudaEventRecord(p->start, st));
+    MSDA_CU(cudaStreamWaitEvent(p->s_in, p->start, 0));
+    MSDA_CU(cudaStreamWaitEvent(p->s_out, p->start, 0));
+    int chunk = 0;
+    for (int n0 = 0; n0 < N; n0 += cb, ++chunk) {
+        const int nb = (N - n0 < cb) ? N - n0 : cb;
+        const int s = chunk % kHostStages;
+        char *base = (char *)workspace + (size_t)s * lay.total;
+        if (chunk >= kHostStages) MSDA_CU(cudaStreamWaitEvent(p->s_in, p->out[s], 0));      // stage drained
+        MSDA_CU(cudaMemcpyAsync(base + lay.value, (const char *)h_value + n0 * vb, nb * vb, cudaMemcpyHostToDevice, p->s_in));
+        MSDA_CU(cudaMemcpyAsync(base + lay.loc, (const char *)h_loc + n0 * lb, nb * lb, cudaMemcpyHostToDevice, p->s_in));
+        MSDA_CU(cudaMemcpyAsync(base + lay.attn, (const char *)h_attn + n0 * ab, nb * ab, cudaMemcpyHostToDevice, p->s_in));
+        MSDA_CU(cudaMemcpyAsync(base + lay.grad_out, (const char *)h_grad_out + n0 * ob, nb * ob, cudaMemcpyHostToDevice, p->s_in));
+        MSDA_CU(cudaEventRecord(p->in[s], p->s_in));
+        MSDA_CU(cudaStreamWaitEvent(st, p->in[s], 0));
+        Dims dc = c.d;
+        dc.N = nb;
+        int rc = c.empty_out ? 0 : launch_forward(dt, base + lay.value, shapes, lsi, base + lay.loc, base + lay.attn,
+                                                  base + lay.out, dc, true, st);
+        if (rc) return cuda_result(rc, fn);
+        rc = launch_backward(dt, base + lay.value, shapes, lsi, base + lay.loc, base + lay.attn, base + lay.grad_out,
+                             base + lay.gv, base + lay.gl, base + lay.ga, dc, true, st);
+        if (rc) return cuda_result(rc, fn);
+        MSDA_CU(cudaEventRecord(p->cmp[s], st));
+        MSDA_CU(cudaStreamWaitEvent(p->s_out, p->cmp[s], 0));
+        MSDA_CU(cudaMemcpyAsync((char *)h_out + n0 * ob, base + lay.out, nb * ob, cudaMemcpyDeviceToHost, p->s_out));
+        MSDA_CU(cudaMemcpyAsync((char *)h_gv + n0 * gvb, base + lay.gv, nb * gvb, cudaMemcpyDeviceToHost, p->s_out));
+        MSDA_CU(cudaMemcpyAsync((char *)h_gl + n0 * lb, base + lay.gl, nb * lb, cudaMemcpyDeviceToHost, p->s_out));
+        MSDA_CU(cudaMemcpyAsync((char *)h_ga + n0 * ab, base + lay.ga, nb * ab, cudaMemcpyDeviceToHost, p->s_out));
+        MSDA_CU(cudaEventRecord(p->out[s], p->s_out));
+    }
+    MSDA_CU(cudaEventRecord(p->done, p->s_out));
+    MSDA_CU(cudaStreamWaitEvent(st, p->done, 0));
+    return cuda_result(0, fn);
+}
+
 }  // namespace msda
 
 using namespace msda;
@@ -189,6 +323,25 @@ int msda_backward_fused_bf16(FUSED_BWD_ARGS)
                       sampling_offsets, attn_logits, grad_out, grad_value, grad_offsets, grad_logits, N, S, M, D, L, Lq, P, stream);
 }
 
+#define HOST_ARGS                                                                                              \
+    const void *h_value, const int64_t *spatial_shapes, const int64_t *level_start_index, const void *h_sampling_loc, \
+        const void *h_attn_weight, const void *h_grad_out, void *h_out, void *h_grad_value, void *h_grad_loc,  \
+        void *h_grad_attn, void *workspace, size_t workspace_bytes, int N, int S, int M, int D, int L, int Lq, \
+        int P, int images_per_chunk, void *stream
+#define HOST_PASS                                                                                              \
+    h_value, spatial_shapes, level_start_index, h_sampling_loc, h_attn_weight, h_grad_out, h_out, h_grad_value, \
+        h_grad_loc, h_grad_attn, workspace, workspace_bytes, N, S, M, D, L, Lq, P, images_per_chunk, stream
+
+int msda_host_step_f32(HOST_ARGS) { return host_step_impl("msda_host_step_f32", DType::F32, HOST_PASS); }
+int msda_host_step_bf16(HOST_ARGS) { return host_step_impl("msda_host_step_bf16", DType::BF16, HOST_PASS); }
+
+size_t msda_host_step_workspace_bytes(int is_bf16, int S, int M, int D, int L, int Lq, int P, int images_per_chunk)
+{
+    if (S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0 || images_per_chunk < 1) return 0;
+    const Dims d{images_per_chunk, S, M, D, L, Lq, P};
+    return (size_t)kHostStages * host_stage_layout(is_bf16 ? DType::BF16 : DType::F32, d, images_per_chunk).total;
+}
+
 int msda_abi_version(void) { return MSDA_ABI_VERSION; }
 
 const char *msda_build_info(void)
@@ -234,6 +387,14 @@ const char *msda_describe_forward(int dtype_bits, int is_bf16, int D, int L, int
 const char *msda_describe_backward(int dtype_bits, int is_bf16, int D, int L, int P)
 {
     return backward_kernel_name(dtype_of(dtype_bits, is_bf16), D, L, P, true);
+}
+
+const char *msda_describe_backward_lq(int dtype_bits, int is_bf16, int D, int L, int P, int Lq)
+{
+    const DType dt = dtype_of(dtype_bits, is_bf16);
+    const Dims d{1, 1, 1, D, L, Lq, P};
+    if (binned_backward_applies(d, dt, true)) return dt == DType::BF16 ? "bwd_bin_bf16" : "bwd_bin_f32";
+    return backward_kernel_name(dt, D, L, P, true);
 }
 
 }  // extern "C"

@@ -600,6 +600,33 @@ def _guard_bands(msda, cuda_device, dtype, shape):
     assert O.rel_l2(views["ga"], rga) <= tol["ga"]
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("per_chunk", [1, 2, 5])
+def test_host_buffer_step_matches_device_path(msda, cuda_device, dtype, per_chunk):
+    """msda_host_step_*: pinned host tensors in, pinned host results out, pipelined over the batch (7 images:
+    more chunks than pipeline stages, a ragged last chunk).  Same kernels as the device path: out, grad_loc and
+    grad_attn bitwise equal, grad_value up to summation order."""
+    shapes, N, M, D, Lq, P = [(12, 40), (6, 20), (3, 10), (2, 5)], 7, 8, 32, 131, 4
+    value, sh, lsi, loc, attn, grad_out = _random_case(55, shapes, N, M, D, Lq, P)
+    v, g = value.to(dtype), grad_out.to(dtype)
+    l, a = loc.float(), attn.float()
+    want = run_ours(msda, v, sh, lsi, l, a, g)
+    dev = cuda_device
+    out, gv, gl, ga = msda.host_step(v.pin_memory(), sh.to(dev), lsi.to(dev), l.pin_memory(), a.pin_memory(),
+                                     g.reshape(N, Lq, M * D).pin_memory(), images_per_chunk=per_chunk)
+    assert not out.is_cuda and out.dtype == dtype and gv.dtype == torch.float32
+    assert torch.equal(out, want[0]) and torch.equal(gl, want[2]) and torch.equal(ga, want[3])
+    assert O.rel_l2(gv, want[1]) < (1e-5 if dtype == torch.float32 else 1e-2)
+    # a second call reuses the cached workspace and the caller's result buffers
+    res2 = msda.host_step(v.pin_memory(), sh.to(dev), lsi.to(dev), l.pin_memory(), a.pin_memory(),
+                          g.reshape(N, Lq, M * D).pin_memory(), images_per_chunk=per_chunk, results=(out, gv, gl, ga))
+    assert res2[0] is out and torch.equal(out, want[0])
+    with pytest.raises(RuntimeError):
+        msda.host_step(v.to(dev), sh.to(dev), lsi.to(dev), l, a, g.reshape(N, Lq, M * D))       # device tensor: wrong entry point
+    with pytest.raises(NotImplementedError):
+        msda.host_step(v, sh, lsi, l, a, g.reshape(N, Lq, M * D))                                # no device anywhere
+
+
 def test_side_stream_and_cuda_graph(msda, cuda_device):
     from monosowa_b200 import workloads as W
     d = W.make_inputs(W.config(0, batch=1), device=cuda_device)
