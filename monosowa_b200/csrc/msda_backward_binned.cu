@@ -38,12 +38,12 @@ constexpr int kBinThreads = 256;
 constexpr unsigned kNoEntry = 0xffffffffu;
 constexpr int kBinMinQueries = 1024;  // below this the chunks are too few / too short to pay for the two extra phases
 
-template <int D>
+template <int D, int QCQ = 0>
 struct BinCfg {
     static constexpr int G = D / kChannelsPerLane;
     static constexpr int QPW = 32 / G;
     static constexpr int QPI = (kBinThreads / 32) * QPW;          // queries per pass of the CTA's warps
-    static constexpr int QC = D <= 32 ? 256 : 128;                // queries per CTA
+    static constexpr int QC = QCQ > 0 ? QCQ : (D <= 32 ? 256 : 128);   // queries per CTA
     static constexpr int HIST_HALVES = kMaxBins + 2;              // 16-bit counters, packed two per word
     static constexpr int HIST_WORDS = (HIST_HALVES + 1) / 2;
     static constexpr int G_BYTES = QC * D * 4;
@@ -64,14 +64,14 @@ struct BinPlan {
     int binbase[MSDA_MAX_LEVELS];    // first cell of each binned level
 };
 
-template <typename VT, int D, bool FUSED>
-__global__ void __launch_bounds__(kBinThreads, 3)
+template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3>
+__global__ void __launch_bounds__(kBinThreads, MINB)
 bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn, const VT *__restrict__ grad_out,
                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn,
                const Dims d, const float *__restrict__ ref, const int max_binned)
 {
-    using C = BinCfg<D>;
+    using C = BinCfg<D, QCQ>;
     using RL = RecordLayout<C::G>;
     constexpr int G = C::G, QPW = C::QPW, QPI = C::QPI, QC = C::QC;
 
@@ -353,12 +353,12 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     }
 }
 
-template <typename VT, int D, bool FUSED>
+template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3>
 int run_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
             const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, cudaStream_t st)
 {
-    using C = BinCfg<D>;
-    auto kern = bwd_bin_kernel<VT, D, FUSED>;
+    using C = BinCfg<D, QCQ>;
+    auto kern = bwd_bin_kernel<VT, D, FUSED, QCQ, MINB>;
     static bool prepared[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -385,7 +385,11 @@ int dispatch_bin(const void *value, const int64_t *shapes, const int64_t *lsi, c
 {
     switch (d.D) {
     case 16: return run_bin<VT, 16, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
-    case 32: return run_bin<VT, 32, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+    // chunk size / register cap were swept on B200 (profiles/r01b_sweep_binned_flavours.jsonl): 256 queries at 80
+    // registers (3 CTAs/SM) wins; 128- or 160-query chunks at 64 registers (4 CTAs/SM) and 128 registers (2 CTAs/SM)
+    // are 6-10 % slower
+    case 32:
+        return run_bin<VT, 32, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
     case 64: return run_bin<VT, 64, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
     }
     return kUnsupported;
