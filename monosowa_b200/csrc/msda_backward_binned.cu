@@ -12,10 +12,9 @@
 //            sample on a coarse ("binned") level the owning lane instead drops a 16-byte entry
 //            {a, lx, ly, cell | rank} into shared memory and counts it in a histogram over the base-corner
 //            cells of the level -- a (H+1)x(W+1) lattice, the corner (y0, x0) ranges over [-1,H-1]x[-1,W-1].
-//            The chunk's grad_out rows are parked in shared memory as well.
 //   phase B  exclusive scan of the histogram, then a counting-sort permutation of the entry indices.
 //   phase C  one lane group per non-empty cell: all samples of a cell share their four corner pixels, so the
-//            group reads each sample's grad_out row once from shared memory, accumulates the four corner
+//            group reads each sample's grad_out row once (L1/L2 -- phase A just read it), accumulates the four corner
 //            rows ((wy*wx)*a)*g in registers and sends FOUR REDG lines per touched cell per chunk.
 //
 // Which levels are binned is decided on the device from spatial_shapes (the host never reads them):
@@ -38,7 +37,7 @@ constexpr int kBinThreads = 256;
 constexpr unsigned kNoEntry = 0xffffffffu;
 constexpr int kBinMinQueries = 1024;  // below this the chunks are too few / too short to pay for the two extra phases
 
-template <int D, int QCQ = 0>
+template <int D, int QCQ = 0, bool GS = false>
 struct BinCfg {
     static constexpr int G = D / kChannelsPerLane;
     static constexpr int QPW = 32 / G;
@@ -46,7 +45,7 @@ struct BinCfg {
     static constexpr int QC = QCQ > 0 ? QCQ : (D <= 32 ? 256 : 128);   // queries per CTA
     static constexpr int HIST_HALVES = kMaxBins + 2;              // 16-bit counters, packed two per word
     static constexpr int HIST_WORDS = (HIST_HALVES + 1) / 2;
-    static constexpr int G_BYTES = QC * D * 4;
+    static constexpr int G_BYTES = GS ? QC * D * 4 : 0;          // the chunk's grad_out rows (GS) or re-read from L1/L2
     static constexpr int ENT_BYTES = QC * kBinSamples * 16;
     static constexpr int HIST_BYTES = ((HIST_WORDS * 4 + 15) / 16) * 16;
     static constexpr int REC_BYTES = (kBinThreads / 32) * RecordLayout<G>::WARP_WORDS * 4;
@@ -64,14 +63,14 @@ struct BinPlan {
     int binbase[MSDA_MAX_LEVELS];    // first cell of each binned level
 };
 
-template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3>
+template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false>
 __global__ void __launch_bounds__(kBinThreads, MINB)
 bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn, const VT *__restrict__ grad_out,
                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn,
                const Dims d, const float *__restrict__ ref, const int max_binned)
 {
-    using C = BinCfg<D, QCQ>;
+    using C = BinCfg<D, QCQ, GS>;
     using RL = RecordLayout<C::G>;
     constexpr int G = C::G, QPW = C::QPW, QPI = C::QPI, QC = C::QC;
 
@@ -134,8 +133,12 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
         const long qm = ((long)n * d.Lq + (qvalid ? q0 + ql : q0)) * d.M + m;
 
         float g[4];
-        Vec4<VT>::load_stream(grad_out + qm * D + gl * kChannelsPerLane, g);
-        *reinterpret_cast<float4 *>(s_g + ql * D + gl * kChannelsPerLane) = make_float4(g[0], g[1], g[2], g[3]);
+        if constexpr (GS) {
+            Vec4<VT>::load_stream(grad_out + qm * D + gl * kChannelsPerLane, g);
+            *reinterpret_cast<float4 *>(s_g + ql * D + gl * kChannelsPerLane) = make_float4(g[0], g[1], g[2], g[3]);
+        } else {
+            Vec4<VT>::load(grad_out + qm * D + gl * kChannelsPerLane, g);      // read again by phase C: keep it cached
+        }
 
         float aw[kMaxBatches];
         float pa[kMaxBatches], pg[kMaxBatches];
@@ -314,6 +317,7 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     const unsigned gmask = (G == 32) ? kFullMask : (((1u << G) - 1u) << (lane & ~(G - 1)));
     const int nbins = s_plan.nbins, lb = s_plan.lb;
     const float *gq = s_g + gl * kChannelsPerLane;
+    const VT *gq_global = grad_out + (((long)n * d.Lq + q0) * d.M + m) * D + gl * kChannelsPerLane;
     for (;;) {
         int c = 0;
         if (gl == 0) c = atomicAdd(&s_next, 1);
@@ -333,7 +337,14 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
         for (int i = i0; i < i1; ++i) {
             const int e = s_idx[i];
             const uint4 en = s_ent[e];
-            const float4 gg = *reinterpret_cast<const float4 *>(gq + (e / kBinSamples) * D);
+            float4 gg;
+            if constexpr (GS) {
+                gg = *reinterpret_cast<const float4 *>(gq + (e / kBinSamples) * D);
+            } else {
+                float gt[4];
+                Vec4<VT>::load(gq_global + (long)(e / kBinSamples) * xs, gt);
+                gg = make_float4(gt[0], gt[1], gt[2], gt[3]);
+            }
             const float a = __uint_as_float(en.x), lx = __uint_as_float(en.y), ly = __uint_as_float(en.z);
             const float hy = 1.f - ly, hx = 1.f - lx;
             const float w00 = (hy * hx) * a, w01 = (hy * lx) * a, w10 = (ly * hx) * a, w11 = (ly * lx) * a;
@@ -353,12 +364,12 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     }
 }
 
-template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3>
+template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false>
 int run_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
             const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, cudaStream_t st)
 {
-    using C = BinCfg<D, QCQ>;
-    auto kern = bwd_bin_kernel<VT, D, FUSED, QCQ, MINB>;
+    using C = BinCfg<D, QCQ, GS>;
+    auto kern = bwd_bin_kernel<VT, D, FUSED, QCQ, MINB, GS>;
     static bool prepared[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -385,10 +396,17 @@ int dispatch_bin(const void *value, const int64_t *shapes, const int64_t *lsi, c
 {
     switch (d.D) {
     case 16: return run_bin<VT, 16, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
-    // chunk size / register cap were swept on B200 (profiles/r01b_sweep_binned_flavours.jsonl): 256 queries at 80
-    // registers (3 CTAs/SM) wins; 128- or 160-query chunks at 64 registers (4 CTAs/SM) and 128 registers (2 CTAs/SM)
-    // are 6-10 % slower
+    // chunk size / register cap / where the chunk's grad_out rows live were swept on B200
+    // (profiles/r01b_sweep_binned_flavours*.jsonl): 256 queries at 80 registers (3 CTAs/SM) with grad_out re-read
+    // through L1/L2 in phase C wins -- parking the rows in shared memory (GS, +32 KB per CTA) shrinks L1 to ~28 KB and
+    // costs 3 %; 64 registers (4 CTAs/SM), 128 registers (2 CTAs/SM) and 128/160/320/512-query chunks are 1-10 % slower
     case 32:
+        if constexpr (!FUSED) {                          // A/B flavours kept for the record (see the sweep files)
+            switch (tuning().bwd_variant) {
+            case 21: return run_bin<VT, 32, FUSED, 256, 3, true>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+            case 23: return run_bin<VT, 32, FUSED, 384, 3, false>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+            }
+        }
         return run_bin<VT, 32, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
     case 64: return run_bin<VT, 64, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
     }
@@ -403,7 +421,7 @@ bool binned_backward_applies(const Dims &d, DType dt, bool vec_ok)
     const int v = tuning().bwd_variant;
     if (!vec_ok || dt == DType::F64 || !(d.D == 16 || d.D == 32 || d.D == 64)) return false;
     if ((long)d.S * d.M * d.D >= (1L << 31) || d.L * d.P < 1) return false;
-    if (v == 20) return true;
+    if (v == 20 || v == 21 || v == 23) return true;
     return v == -1 && d.Lq >= kBinMinQueries;
 }
 

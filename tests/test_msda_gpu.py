@@ -271,7 +271,8 @@ BIN_CASES = [
 
 @pytest.mark.parametrize("case", BIN_CASES, ids=lambda c: f"M{c[2]}D{c[3]}Lq{c[4]}P{c[5]}L{len(c[0])}")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_binned_backward_vs_oracle_and_direct(msda, case, dtype):
+@pytest.mark.parametrize("variant", [20, 21, 23])
+def test_binned_backward_vs_oracle_and_direct(msda, case, dtype, variant):
     """the binned kernel against the fp64 oracle, and against the record kernel: grad_loc / grad_attn come from
     identical arithmetic (bitwise equal), grad_value differs only in summation order."""
     shapes, N, M, D, Lq, P = case
@@ -279,7 +280,7 @@ def test_binned_backward_vs_oracle_and_direct(msda, case, dtype):
     L = msda._lib
     ct = torch.float32
     try:
-        L.set_tuning("bwd_variant", 20)
+        L.set_tuning("bwd_variant", variant)
         check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=f"binned {case}")
         b = run_ours(msda, value.to(dtype), sh, lsi, loc.to(ct), attn.to(ct), grad_out.to(dtype))
         L.set_tuning("bwd_variant", 11)
