@@ -63,7 +63,7 @@ struct BinPlan {
     int binbase[MSDA_MAX_LEVELS];    // first cell of each binned level
 };
 
-template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false>
+template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false, int LDQ = 1, int LOADH = 0>
 __global__ void __launch_bounds__(kBinThreads, MINB)
 bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn, const VT *__restrict__ grad_out,
@@ -73,6 +73,7 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     using C = BinCfg<D, QCQ, GS>;
     using RL = RecordLayout<C::G>;
     constexpr int G = C::G, QPW = C::QPW, QPI = C::QPI, QC = C::QC;
+    constexpr int LD = (LDQ <= G / 2) ? LDQ : G / 2;     // samples whose loads are issued together
 
     extern __shared__ __align__(16) unsigned char smem[];
     float *s_g = reinterpret_cast<float *>(smem);
@@ -185,31 +186,47 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 float t[4 * GH];
+                // LD samples are loaded together (4*LD independent LDG.128 in flight per lane) before any of them is
+                // consumed.  The ncu source view shows 44 % of the stall samples as long-scoreboard waits on the first
+                // FFMA of each sample, yet LD = 1 is the measured optimum: LD = 2 / 4 are 25-90 % SLOWER with or without
+                // L1 allocation (profiles/r01b_sweep_load_grouping.jsonl) -- the latency is queueing in a saturated
+                // memory system, not exposed idle time, and deeper bursts only lengthen the queues.
 #pragma unroll
-                for (int u = 0; u < GH; ++u) {
-                    const int s = h * GH + u;
-                    t[4 * u] = t[4 * u + 1] = t[4 * u + 2] = t[4 * u + 3] = 0.f;
-                    const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
-                    const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
-                    if (d.S > 0) {
-                        float v00[4], v01[4], v10[4], v11[4];
-                        Vec4<VT>::template gather<0>(vimg + off.x, v00);
-                        Vec4<VT>::template gather<0>(vimg + off.y, v01);
-                        Vec4<VT>::template gather<0>(vimg + off.z, v10);
-                        Vec4<VT>::template gather<0>(vimg + off.w, v11);
+                for (int u0 = 0; u0 < GH; u0 += LD) {
+                    int4 off[LD];
+                    float4 wa[LD];
+                    float v[LD][4][4];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            t[4 * u] += g[c] * v00[c];
-                            t[4 * u + 1] += g[c] * v01[c];
-                            t[4 * u + 2] += g[c] * v10[c];
-                            t[4 * u + 3] += g[c] * v11[c];
+                    for (int j = 0; j < LD; ++j) {
+                        const int s = h * GH + u0 + j;
+                        off[j] = *reinterpret_cast<const int4 *>(grp + s * 4);
+                        wa[j] = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
+                        if (d.S > 0) {
+                            Vec4<VT>::template gather<LOADH>(vimg + off[j].x, v[j][0]);
+                            Vec4<VT>::template gather<LOADH>(vimg + off[j].y, v[j][1]);
+                            Vec4<VT>::template gather<LOADH>(vimg + off[j].z, v[j][2]);
+                            Vec4<VT>::template gather<LOADH>(vimg + off[j].w, v[j][3]);
                         }
                     }
-                    if (b0 + s < lbP) {                  // fine level (warp-uniform): direct reductions
-                        if (wa.x != 0.f) red_add_f32x4(gvimg + off.x, wa.x * g[0], wa.x * g[1], wa.x * g[2], wa.x * g[3]);
-                        if (wa.y != 0.f) red_add_f32x4(gvimg + off.y, wa.y * g[0], wa.y * g[1], wa.y * g[2], wa.y * g[3]);
-                        if (wa.z != 0.f) red_add_f32x4(gvimg + off.z, wa.z * g[0], wa.z * g[1], wa.z * g[2], wa.z * g[3]);
-                        if (wa.w != 0.f) red_add_f32x4(gvimg + off.w, wa.w * g[0], wa.w * g[1], wa.w * g[2], wa.w * g[3]);
+#pragma unroll
+                    for (int j = 0; j < LD; ++j) {
+                        const int u = u0 + j, s = h * GH + u;
+                        t[4 * u] = t[4 * u + 1] = t[4 * u + 2] = t[4 * u + 3] = 0.f;
+                        if (d.S > 0) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                t[4 * u] += g[c] * v[j][0][c];
+                                t[4 * u + 1] += g[c] * v[j][1][c];
+                                t[4 * u + 2] += g[c] * v[j][2][c];
+                                t[4 * u + 3] += g[c] * v[j][3][c];
+                            }
+                        }
+                        if (b0 + s < lbP) {                  // fine level (warp-uniform): direct reductions
+                            if (wa[j].x != 0.f) red_add_f32x4(gvimg + off[j].x, wa[j].x * g[0], wa[j].x * g[1], wa[j].x * g[2], wa[j].x * g[3]);
+                            if (wa[j].y != 0.f) red_add_f32x4(gvimg + off[j].y, wa[j].y * g[0], wa[j].y * g[1], wa[j].y * g[2], wa[j].y * g[3]);
+                            if (wa[j].z != 0.f) red_add_f32x4(gvimg + off[j].z, wa[j].z * g[0], wa[j].z * g[1], wa[j].z * g[2], wa[j].z * g[3]);
+                            if (wa[j].w != 0.f) red_add_f32x4(gvimg + off[j].w, wa[j].w * g[0], wa[j].w * g[1], wa[j].w * g[2], wa[j].w * g[3]);
+                        }
                     }
                 }
                 group_reduce_scatter<G, 4 * GH>(t, gl);
@@ -364,12 +381,12 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     }
 }
 
-template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false>
+template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false, int LDQ = 1, int LOADH = 0>
 int run_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
             const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, cudaStream_t st)
 {
     using C = BinCfg<D, QCQ, GS>;
-    auto kern = bwd_bin_kernel<VT, D, FUSED, QCQ, MINB, GS>;
+    auto kern = bwd_bin_kernel<VT, D, FUSED, QCQ, MINB, GS, LDQ, LOADH>;
     static bool prepared[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -405,6 +422,7 @@ int dispatch_bin(const void *value, const int64_t *shapes, const int64_t *lsi, c
             switch (tuning().bwd_variant) {
             case 21: return run_bin<VT, 32, FUSED, 256, 3, true>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
             case 23: return run_bin<VT, 32, FUSED, 384, 3, false>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+            case 24: return run_bin<VT, 32, FUSED, 256, 3, false, 2>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
             }
         }
         return run_bin<VT, 32, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
@@ -421,7 +439,7 @@ bool binned_backward_applies(const Dims &d, DType dt, bool vec_ok)
     const int v = tuning().bwd_variant;
     if (!vec_ok || dt == DType::F64 || !(d.D == 16 || d.D == 32 || d.D == 64)) return false;
     if ((long)d.S * d.M * d.D >= (1L << 31) || d.L * d.P < 1) return false;
-    if (v == 20 || v == 21 || v == 23) return true;
+    if (v == 20 || v == 21 || v == 23 || v == 24) return true;
     return v == -1 && d.Lq >= kBinMinQueries;
 }
 

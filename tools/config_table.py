@@ -34,7 +34,7 @@ def main():
             frac_of_measured_hbm=round(ab["total"] / (f + b) / 1e6 / 6559.4, 4),
             alg_MB=round(ab["total"] / 1e6, 1),
             kernels=[lib.msda_describe_forward(32, int(bf), wl.head_dim, wl.L, wl.points).decode(),
-                     lib.msda_describe_backward(32, int(bf), wl.head_dim, wl.L, wl.points).decode()])), flush=True)
+                     lib.msda_describe_backward_lq(32, int(bf), wl.head_dim, wl.L, wl.points, wl.Lq).decode()])), flush=True)
         del d, a5
         torch.cuda.empty_cache()
 

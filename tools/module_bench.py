@@ -18,8 +18,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--set", default="", help="comma-separated key=value for msda_set_tuning")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
+    for kv in filter(None, a.set.split(",")):
+        k_, v_ = kv.split("=")
+        msda._lib.set_tuning(k_, int(v_))
     torch.manual_seed(0)
     sh, lsi = W.level_tensors(W.KITTI, dev)
     S = 10200
@@ -49,7 +53,7 @@ def main():
             with torch.no_grad():
                 f = timeit(fwd, a.iters)
             fb = timeit(fwd_bwd, a.iters)
-            print(json.dumps(dict(module="MSDeformAttn", batch=a.batch, queries=S, autocast_bf16=amp, fused_preprocessing=fused,
+            print(json.dumps(dict(module="MSDeformAttn", tuning=a.set or "default", batch=a.batch, queries=S, autocast_bf16=amp, fused_preprocessing=fused,
                                   fwd_ms=round(f, 3), fwd_bwd_ms=round(fb, 3), peak_mem_GB=round(torch.cuda.max_memory_allocated() / 2**30, 2))),
                   flush=True)
             torch.cuda.reset_peak_memory_stats()
