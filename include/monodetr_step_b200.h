@@ -1,0 +1,55 @@
+/* monodetr_step_b200.h -- C ABI of libmonodetr_step_b200.so: device-side pieces of the MonoDETR training
+ * step that the reference runs on the host between kernels.
+ *
+ * Not part of the MSDA operator (include/msda_b200.h); a separate library so that the operator's ABI stays
+ * exactly what the reference's extension exported.  Same conventions: plain pointers and sizes, caller owns
+ * all memory, the stream is passed in, no host synchronisation, 0 on success / negative argument error /
+ * positive cudaError_t, detr_step_last_error() for the message.
+ */
+#ifndef MONODETR_STEP_B200_H_
+#define MONODETR_STEP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DETR_STEP_MAX_IMAGES 256 /* per call; image sizes travel as kernel arguments (no device copy, no sync) */
+
+enum {
+    DETR_STEP_OK = 0,
+    DETR_STEP_ERR_NULL_POINTER = -1,
+    DETR_STEP_ERR_BAD_SHAPE = -2,
+    DETR_STEP_ERR_UNSUPPORTED = -4 /* a sub-problem does not fit the kernel's shared memory: use the host path */
+};
+
+/* Group-wise Hungarian matching on the device.
+ *
+ * Replaces the host section of HungarianMatcher.forward -- MonoDETR/lib/models/monodetr/matcher.py:87-104:
+ * there the cost matrix is copied to the host (`C.cpu()`, a device synchronisation per decoder layer) and
+ * scipy.optimize.linear_sum_assignment runs once per image and query group (16 x 11 calls per layer).
+ *
+ *   cost        DEVICE float [B, Q, T]: matching cost of query q of image b against target t, where T is the
+ *               number of targets of the WHOLE batch (matcher.py:86); image b owns the columns
+ *               [sum(sizes[:b]), sum(sizes[:b+1])).
+ *   sizes       HOST int [B]: targets per image (known on the host: len(t["boxes"])); read during the call.
+ *   groups      query groups (matcher.py:93): the Q queries are split into `groups` consecutive blocks of
+ *               Q / groups, each matched against the image's targets independently.
+ *   out_query / out_target
+ *               DEVICE int64 [groups * sum_b min(sizes[b], Q / groups)]: per image one block of
+ *               groups * k_b pairs (k_b = min(sizes[b], Q / groups)), group after group, inside a group ordered
+ *               by query index -- i.e. exactly the concatenation matcher.py:99-103 builds from scipy's
+ *               (row_ind, col_ind); out_query already carries the group offset g * (Q / groups).
+ * The assignment is the exact minimum (shortest augmenting paths with fp64 potentials, like scipy's
+ * rectangular solver); for cost matrices without exact ties it is THE optimum, hence identical to scipy's.
+ * One warp per (image, group) sub-problem. */
+int detr_group_lsa_f32(const float *cost, const int *sizes, int B, int Q, int T, int groups,
+                       int64_t *out_query, int64_t *out_target, void *stream);
+
+const char *detr_step_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONODETR_STEP_B200_H_ */

@@ -21,7 +21,11 @@ CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libmsda_b200.so")
 SOURCES = ["msda_forward.cu", "msda_backward.cu", "msda_backward_binned.cu", "msda_capi.cu"]
-HEADERS = [os.path.join(CSRC, "msda_common.cuh"), os.path.join(CSRC, "msda_records.cuh"), os.path.join(ROOT, "include", "msda_b200.h")]
+HEADERS = [os.path.join(CSRC, "msda_common.cuh"), os.path.join(CSRC, "msda_records.cuh"), os.path.join(ROOT, "include", "msda_b200.h"),
+           os.path.join(ROOT, "include", "monodetr_step_b200.h")]
+# second library: device-side pieces of the MonoDETR training step, kept out of the operator's ABI
+STEP_LIB = os.path.join(PKG, "libmonodetr_step_b200.so")
+STEP_SOURCES = ["step_lsa.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
@@ -57,22 +61,34 @@ def _compile(nvcc: str, src: str, verbose: bool) -> str:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    if not force and not _stale(LIB, [*srcs, *HEADERS, os.path.abspath(__file__)]):
-        return LIB
+def _build_one(lib: str, sources, force: bool, verbose: bool) -> str:
+    srcs = [os.path.join(CSRC, s) for s in sources]
+    if not force and not _stale(lib, [*srcs, *HEADERS, os.path.abspath(__file__)]):
+        return lib
     nvcc = nvcc_path()
     os.makedirs(BUILD, exist_ok=True)
     if force:
-        for f in os.listdir(BUILD):
-            os.remove(os.path.join(BUILD, f))
-    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(lambda s: _compile(nvcc, s, verbose), SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        for s in sources:
+            for f in (os.path.splitext(s)[0] + ".o", os.path.splitext(s)[0] + ".o.log"):
+                if os.path.exists(os.path.join(BUILD, f)):
+                    os.remove(os.path.join(BUILD, f))
+    with cf.ThreadPoolExecutor(max_workers=len(sources)) as ex:
+        objs = list(ex.map(lambda s: _compile(nvcc, s, verbose), sources))
+    cmd = [nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """libmsda_b200.so (the operator) -- returns its path; also keeps libmonodetr_step_b200.so up to date."""
+    _build_one(STEP_LIB, STEP_SOURCES, force, verbose)
+    return _build_one(LIB, SOURCES, force, verbose)
+
+
+def build_step(force: bool = False, verbose: bool = False) -> str:
+    return _build_one(STEP_LIB, STEP_SOURCES, force, verbose)
 
 
 if __name__ == "__main__":

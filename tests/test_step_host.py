@@ -1,0 +1,227 @@
+"""SURVEY.md 8 row f3 -- device-resident replacements of the training step's host sections
+(monosowa_b200/step_host).  CPU tests check the vectorised painters and the multi-tensor AdamW against literal
+restatements of the reference loops; GPU tests check the assignment kernel against scipy (the reference's solver)
+and the whole matcher against the staged reference matcher when baseline/_ref is present."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+# ---- literal restatements of the reference loops (test-side checkers) -----------------------------------------
+def ref_depth_targets(depth_logits, gt_boxes2d, gt_center_depth, num_gt_per_img):
+    """depth_predictor/ddn_loss/ddn_loss.py:42-64, statement by statement"""
+    B, _, H, W = depth_logits.shape
+    depth_maps = torch.zeros((B, H, W), dtype=depth_logits.dtype)
+    gt_boxes2d[:, :2] = torch.floor(gt_boxes2d[:, :2])
+    gt_boxes2d[:, 2:] = torch.ceil(gt_boxes2d[:, 2:])
+    boxes = gt_boxes2d.long().split(num_gt_per_img, dim=0)
+    depths = gt_center_depth.split(num_gt_per_img, dim=0)
+    for b in range(len(boxes)):
+        d, order = torch.sort(depths[b], dim=0, descending=True)
+        bb = boxes[b][order]
+        for n in range(bb.shape[0]):
+            u1, v1, u2, v2 = (int(x) for x in bb[n])
+            depth_maps[b, v1:v2, u1:u2] = d[n]
+    return depth_maps
+
+
+def ref_fg_mask(gt_boxes2d, shape, num_gt_per_img, downsample_factor=1):
+    """depth_predictor/ddn_loss/balancer.py:52-81"""
+    fg = torch.zeros(shape, dtype=torch.bool)
+    gt_boxes2d /= downsample_factor
+    gt_boxes2d[:, :2] = torch.floor(gt_boxes2d[:, :2])
+    gt_boxes2d[:, 2:] = torch.ceil(gt_boxes2d[:, 2:])
+    boxes = gt_boxes2d.long().split(num_gt_per_img, dim=0)
+    for b in range(len(boxes)):
+        for n in range(boxes[b].shape[0]):
+            u1, v1, u2, v2 = (int(x) for x in boxes[b][n])
+            fg[b, v1:v2, u1:u2] = True
+    return fg
+
+
+def _boxes(seed, num_gt, H=24, W=80, wild=False):
+    g = torch.Generator().manual_seed(seed)
+    n = sum(num_gt)
+    lo = torch.rand(n, 2, generator=g) * torch.tensor([W * 0.8, H * 0.8])
+    wh = torch.rand(n, 2, generator=g) * torch.tensor([W * 0.3, H * 0.5])
+    boxes = torch.cat([lo, lo + wh], 1)
+    if wild:                                                # boxes hanging over every border, degenerate and inverted ones
+        boxes = boxes + (torch.rand(n, 4, generator=g) - 0.5) * torch.tensor([W, H, W, H]) * 1.5
+    depth = torch.rand(n, generator=g) * 60
+    if n > 3:
+        depth[1] = depth[0]                                 # equal depths: the painters must still agree
+    return boxes, depth
+
+
+@pytest.mark.parametrize("num_gt,wild", [([8] * 4, False), ([3, 0, 5, 1], False), ([6, 7, 2], True), ([0, 0], False), ([12], True)])
+def test_painters_match_reference_loops(num_gt, wild):
+    from monosowa_b200.step_host import paint_depth_targets, paint_foreground
+    B, H, W = len(num_gt), 24, 80
+    boxes, depth = _boxes(11 + len(num_gt), num_gt, H, W, wild)
+    logits = torch.zeros(B, 81, H, W)
+    b1, b2 = boxes.clone(), boxes.clone()
+    want = ref_depth_targets(logits, b1, depth, num_gt)
+    got = paint_depth_targets(None, logits, b2, depth, num_gt)
+    assert torch.equal(got, want)
+    assert torch.equal(b1, b2)                              # same in-place snapping of the caller's tensor
+    want_fg = ref_fg_mask(b1, (B, H, W), num_gt)
+    got_fg = paint_foreground(b2, (B, H, W), num_gt, device=torch.device("cpu"))
+    assert torch.equal(got_fg, want_fg)
+
+
+def test_foreach_adamw_matches_reference_loop():
+    """optimizer_helper.py:76-127 restated per parameter vs the multi-tensor step, incl. a parameter that
+    receives no gradient in some steps (its step counter lags) and the two weight-decay groups"""
+    from monosowa_b200.step_host import foreach_adamw_step
+    import types
+
+    class AdamW(torch.optim.Optimizer):                     # same state layout / defaults as the reference class
+        def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
+            super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad))
+
+        def step(self):
+            for group in self.param_groups:
+                for p in group["params"]:
+                    if p.grad is None:
+                        continue
+                    grad, state = p.grad.data, self.state[p]
+                    if len(state) == 0:
+                        state["step"] = 0
+                        state["exp_avg"] = torch.zeros_like(p.data)
+                        state["exp_avg_sq"] = torch.zeros_like(p.data)
+                    beta1, beta2 = group["betas"]
+                    state["step"] += 1
+                    state["exp_avg"].mul_(beta1).add_(grad, alpha=1 - beta1)
+                    state["exp_avg_sq"].mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+                    denom = state["exp_avg_sq"].sqrt().add_(group["eps"])
+                    step_size = group["lr"] * math.sqrt(1 - beta2 ** state["step"]) / (1 - beta1 ** state["step"])
+                    p.data.add_(torch.mul(p.data, group["weight_decay"]).addcdiv_(state["exp_avg"], denom, value=1), alpha=-step_size)
+
+    def make():
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.randn(s)) for s in ((7, 5), (5,), (3, 3, 2), (1,))]
+        return ps, AdamW([{"params": ps[1::2], "weight_decay": 0}, {"params": ps[0::2], "weight_decay": 1e-4}], lr=2e-4)
+
+    pa, oa = make()
+    pb, ob = make()
+    ob.step = types.MethodType(foreach_adamw_step, ob)
+    g = torch.Generator().manual_seed(1)
+    for it in range(6):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if i == 2 and it % 2 == 1:
+                a.grad = b.grad = None                      # this parameter skips every other step
+            else:
+                gr = torch.randn(a.shape, generator=g)
+                a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step()
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
+        assert oa.state[a]["step"] == ob.state[b]["step"]
+        assert torch.allclose(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"], rtol=1e-6, atol=0)
+
+
+def test_step_library_exports_declared_symbols():
+    import ctypes
+    import re
+    from monosowa_b200.step_host import lsa
+    hdr = open(os.path.join(ROOT, "include", "monodetr_step_b200.h")).read()
+    declared = set(re.findall(r"\b(detr_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == {"detr_group_lsa_f32", "detr_step_last_error"}
+    raw = ctypes.CDLL(lsa.LIB_PATH) if os.path.exists(lsa.LIB_PATH) else lsa.lib()
+    for name in declared:
+        assert hasattr(raw, name)
+
+
+# ---- GPU ----------------------------------------------------------------------------------------------------------
+def _scipy_pairs(cost, sizes, groups):
+    """matcher.py:87-104 on the host (the reference's own solver)"""
+    import numpy as np
+    from scipy.optimize import linear_sum_assignment
+    C = cost.cpu()
+    nq = C.shape[1] // groups
+    out = []
+    for b, c in enumerate(C.split(sizes, -1)):
+        qi, ti = [], []
+        for g in range(groups):
+            r, col = linear_sum_assignment(c[b, g * nq:(g + 1) * nq])
+            qi.append(r + g * nq); ti.append(col)
+        out.append((torch.as_tensor(np.concatenate(qi)), torch.as_tensor(np.concatenate(ti))))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [
+    (16, 550, 11, [8] * 16),                       # the training shape: 50 queries per group, 8 targets per image
+    (3, 50, 1, [8, 0, 5]),                         # eval: one group; an image without targets
+    (2, 40, 4, [10, 17]),                          # 10 queries per group: one image square, one with MORE targets than queries
+    (1, 64, 2, [50]),                              # more targets than queries per group (rows = queries)
+    (4, 96, 3, [1, 32, 31, 33]),                   # around the warp width
+    (1, 300, 1, [120]),                            # several columns per lane
+], ids=lambda c: f"B{c[0]}Q{c[1]}G{c[2]}")
+def test_group_lsa_matches_scipy(cuda_device, case):
+    from monosowa_b200.step_host import group_lsa
+    B, Q, groups, sizes = case
+    g = torch.Generator().manual_seed(B * 1000 + Q)
+    cost = (torch.randn(B, Q, sum(sizes), generator=g) * 3).to(cuda_device)
+    got = group_lsa(cost, sizes, groups)
+    want = _scipy_pairs(cost, sizes, groups)
+    assert len(got) == B
+    for (gq, gt), (wq, wt) in zip(got, want):
+        assert gq.dtype == torch.int64 and gq.is_cuda
+        assert torch.equal(gq.cpu(), wq) and torch.equal(gt.cpu(), wt)
+
+
+@pytest.mark.gpu
+def test_group_lsa_cost_is_optimal_with_ties(cuda_device):
+    """integer costs have many exact ties: the assignment may differ from scipy's, its total cost may not"""
+    from monosowa_b200.step_host import group_lsa
+    sizes = [6, 9, 3]
+    cost = torch.randint(0, 4, (3, 60, sum(sizes)), generator=torch.Generator().manual_seed(3)).float().to(cuda_device)
+    got = group_lsa(cost, sizes, 5)
+    want = _scipy_pairs(cost, sizes, 5)
+    off = 0
+    for b, ((gq, gt), (wq, wt)) in enumerate(zip(got, want)):
+        c = cost[b, :, off:off + sizes[b]].cpu()
+        assert len(set(gq.tolist())) == len(gq) and sorted(gt.tolist()) == sorted(wt.tolist())
+        assert float(c[gq.cpu(), gt.cpu()].sum()) == float(c[wq, wt].sum())
+        off += sizes[b]
+
+
+def _staged_reference():
+    ref = os.path.join(ROOT, "baseline", "_ref", "MonoDETR")
+    return ref if os.path.isdir(os.path.join(ref, "lib")) else None
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_staged_reference() is None, reason="baseline/_ref/MonoDETR not staged (tools/stage_reference.py)")
+def test_device_matcher_matches_reference_matcher(cuda_device):
+    """the unmodified reference HungarianMatcher (staged copy) vs DeviceMatcher on the same random predictions"""
+    import importlib.util
+    ref = _staged_reference()
+    sys.path.insert(0, ref)                                 # matcher.py imports utils.box_ops from the reference tree
+    try:                                                    # (loaded by path: the package __init__ would pull in the whole model)
+        spec = importlib.util.spec_from_file_location("_ref_matcher", os.path.join(ref, "lib", "models", "monodetr", "matcher.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["_ref_matcher"] = mod
+        spec.loader.exec_module(mod)
+        HungarianMatcher = mod.HungarianMatcher
+    finally:
+        sys.path.remove(ref)
+    from monosowa_b200.step_host import DeviceMatcher
+    g = torch.Generator().manual_seed(5)
+    bs, nq, sizes = 4, 550, [8, 3, 0, 11]
+    outputs = {"pred_logits": torch.randn(bs, nq, 3, generator=g).to(cuda_device),
+               "pred_boxes": (torch.rand(bs, nq, 6, generator=g) * 0.5 + 0.05).to(cuda_device)}
+    targets = [{"labels": torch.randint(0, 3, (n,), generator=g).to(cuda_device),
+                "boxes": torch.rand(n, 4, generator=g).to(cuda_device),
+                "boxes_3d": (torch.rand(n, 6, generator=g) * 0.5 + 0.05).to(cuda_device)} for n in sizes]
+    matcher = HungarianMatcher(cost_class=2, cost_bbox=5, cost_3dcenter=10, cost_giou=2)
+    want = matcher(outputs, targets, group_num=11)
+    got = DeviceMatcher(matcher)(outputs, targets, group_num=11)
+    for (gq, gt), (wq, wt) in zip(got, want):
+        assert torch.equal(gq.cpu(), wq) and torch.equal(gt.cpu(), wt)

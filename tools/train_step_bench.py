@@ -108,6 +108,11 @@ def main():
     ap.add_argument("--op", default="ours", choices=["ours", "ref_cuda"])
     ap.add_argument("--logging", default="faithful", choices=["faithful", "lean"])
     ap.add_argument("--profile-msda", action="store_true", help="kineto pass: MSDA kernels' share of the step")
+    ap.add_argument("--host-opt", default="none",
+                    help="SURVEY 8 f3: comma list of matcher,ddn,adamw or 'all' -- device-resident replacements of the "
+                         "step's host sections (monosowa_b200.step_host); 'none' = the reference's own code")
+    ap.add_argument("--breakdown", action="store_true",
+                    help="extra pass: per-phase host issue time vs GPU time (forward / criterion / logging / backward / optimizer)")
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="infer: model.eval() forward only (50 queries), as tester_helper.py:80-99")
     ap.add_argument("--amp", default="none", choices=["none", "bf16"],
@@ -140,6 +145,19 @@ def main():
     optimizer = build_optimizer(cfg["optimizer"], model)
     images, calibs, tdict = synthetic_batch(args.batch, dev, seed=1237 + rank)
     targets = prepare_targets(tdict, args.batch)
+    host_opt, host_opt_check = [], None
+    if args.host_opt != "none":
+        from monosowa_b200 import step_host
+        want = {"matcher", "ddn", "adamw"} if args.host_opt == "all" else set(args.host_opt.split(","))
+        with torch.no_grad():                               # same model outputs through the reference criterion ...
+            out0 = model(images, calibs, targets, tdict["img_size"], dn_args=None)
+            ld_ref = {k: float(v) for k, v in criterion(out0, targets, None, None).items()}
+        host_opt = step_host.install(criterion, optimizer, matcher="matcher" in want, ddn="ddn" in want, adamw="adamw" in want)
+        with torch.no_grad():                               # ... and through the patched one: every loss term must agree
+            ld_opt = {k: float(v) for k, v in criterion(out0, targets, None, None).items()}
+        host_opt_check = {"loss_terms": len(ld_ref), "max_abs_diff": max(abs(ld_ref[k] - ld_opt[k]) for k in ld_ref),
+                          "max_rel_diff": max(abs(ld_ref[k] - ld_opt[k]) / max(abs(ld_ref[k]), 1e-12) for k in ld_ref)}
+        del out0
     img_sizes = tdict["img_size"]
     weight_dict = criterion.weight_dict
 
@@ -212,6 +230,63 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 
+    breakdown = None
+    if args.breakdown and args.mode == "train" and rank == 0 and world == 1:
+        # each phase bracketed by CUDA events (GPU time between the phase's first and last kernel incl. idle gaps) and by
+        # perf_counter without a sync (how long the host needs to ISSUE the phase); a phase whose issue time exceeds
+        # its GPU time is host-bound.  `sync_ms` = the same phase followed by a device sync (max of the two).
+        names = ("zero_grad", "forward", "criterion", "logging", "backward", "optimizer")
+        acc = {n: [0.0, 0.0] for n in names}
+        n_bd = 5
+        for i in range(n_bd):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            ts = []
+            torch.cuda.synchronize()
+            evs[0].record(); ts.append(time.perf_counter())
+            optimizer.zero_grad()
+            evs[1].record(); ts.append(time.perf_counter())
+            with amp:
+                outputs = net(images, calibs, targets, img_sizes, dn_args=None)
+            outputs = to_f32(outputs)
+            evs[2].record(); ts.append(time.perf_counter())
+            ld = criterion(outputs, targets, None, None)
+            loss = sum(ld[k] * weight_dict[k] for k in ld.keys() if k in weight_dict)
+            evs[3].record(); ts.append(time.perf_counter())
+            red = misc.reduce_dict(ld)
+            _ = sum((red[k] * weight_dict[k]).item() for k in red if k in weight_dict)
+            evs[4].record(); ts.append(time.perf_counter())
+            loss.backward()
+            evs[5].record(); ts.append(time.perf_counter())
+            optimizer.step()
+            evs[6].record(); ts.append(time.perf_counter())
+            torch.cuda.synchronize()
+            for j, n in enumerate(names):
+                acc[n][0] += (ts[j + 1] - ts[j]) * 1e3 / n_bd
+                acc[n][1] += evs[j].elapsed_time(evs[j + 1]) / n_bd
+        breakdown = {n: {"host_issue_ms": round(v[0], 2), "gpu_span_ms": round(v[1], 2)} for n, v in acc.items()}
+        # inside the criterion: wall time (device-synchronised) of the matcher calls and of each loss term
+        crit_t = {}
+
+        def timed(label, fn):
+            def wrapper(*a, **k):
+                torch.cuda.synchronize(); t0_ = time.perf_counter()
+                r = fn(*a, **k)
+                torch.cuda.synchronize()
+                crit_t[label] = crit_t.get(label, 0.0) + (time.perf_counter() - t0_) * 1e3 / n_bd
+                return r
+            return wrapper
+
+        orig_matcher, orig_get_loss = criterion.matcher.forward, criterion.get_loss
+        criterion.matcher.forward = timed("matcher(x3)", orig_matcher)
+        criterion.get_loss = lambda loss, *a, **k: timed("loss:" + loss, orig_get_loss)(loss, *a, **k)
+        with torch.no_grad():
+            for i in range(n_bd):
+                with amp:
+                    outputs = net(images, calibs, targets, img_sizes, dn_args=None)
+                criterion(to_f32(outputs), targets, None, None)
+        criterion.matcher.forward, criterion.get_loss = orig_matcher, orig_get_loss
+        breakdown["criterion_parts_ms"] = {k: round(v, 2) for k, v in sorted(crit_t.items(), key=lambda kv: -kv[1])}
+
     share = None
     if args.profile_msda and rank == 0:
         from torch.profiler import ProfilerActivity, profile
@@ -240,9 +315,9 @@ def main():
             "ms_per_step_wall": wallms, "scaling": "weak", "higher_is_better": True, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE.json configs[3]: unmodified reference MonoDETR (ResNet-50, 3 enc + 3 dec layers) + "
                                    "SetCriterion + reference AdamW, synthetic KITTI batch", "batch_per_gpu": args.batch,
-                       "global_batch": args.batch * world, "image": [384, 1280], "msda_op": args.op, "logging": args.logging, "mode": args.mode, "amp": args.amp,
+                       "global_batch": args.batch * world, "image": [384, 1280], "msda_op": args.op, "host_opt": host_opt, "host_opt_check": host_opt_check, "logging": args.logging, "mode": args.mode, "amp": args.amp,
                        "parallelism": f"ddp{world}", "trainable_params": n_params},
-            "loss": float(loss), "msda": share}), flush=True)
+            "loss": float(loss), "msda": share, "breakdown": breakdown}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
