@@ -192,6 +192,17 @@ def test_group_lsa_cost_is_optimal_with_ties(cuda_device):
         off += sizes[b]
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("cols", [2, 4])
+def test_pairwise_l1_is_bitwise_cdist(cuda_device, cols):
+    from monosowa_b200.step_host import pairwise_l1
+    g = torch.Generator().manual_seed(cols)
+    for n, m in ((8800, 128), (550, 8), (37, 1), (5, 300)):
+        a = torch.rand(n, cols, generator=g).to(cuda_device)
+        b = torch.rand(m, cols, generator=g).to(cuda_device)
+        assert torch.equal(pairwise_l1(a, b), torch.cdist(a, b, p=1)), (n, m, cols)
+
+
 def _staged_reference():
     ref = os.path.join(ROOT, "baseline", "_ref", "MonoDETR")
     return ref if os.path.isdir(os.path.join(ref, "lib")) else None

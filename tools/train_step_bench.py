@@ -301,8 +301,11 @@ def main():
                 tot += dt
                 if "msda::" in e.key or "ms_deformable" in e.key or "rec_kernel" in e.key or "vec_kernel" in e.key:
                     msda_t += dt
+        top = sorted(((getattr(e, "device_time_total", 0.0) or getattr(e, "cuda_time_total", 0.0), e.count, e.key)
+                      for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA), reverse=True)[:25]
         share = {"gpu_kernel_ms_per_step": tot / 3e3, "msda_kernel_ms_per_step": msda_t / 3e3,
-                 "msda_share_of_gpu_time": msda_t / tot if tot else None}
+                 "msda_share_of_gpu_time": msda_t / tot if tot else None,
+                 "top_kernels_ms_per_step": [[round(t / 3e3, 3), c // 3, k[:90]] for t, c, k in top]}
     elif args.profile_msda and world > 1:
         for i in range(3):
             step(i + 1)                                          # keep the ranks in lock step
