@@ -55,4 +55,12 @@ def group_lsa(cost: torch.Tensor, sizes, groups: int):
             return None
         if rc:
             raise RuntimeError(f"detr_group_lsa_f32 failed (code {rc}): {lib().detr_step_last_error().decode()}")
-    return list(zip(out_q.split(per_image), out_t.split(per_image)))
+    pairs = MatchList(zip(out_q.split(per_image), out_t.split(per_image)))
+    pairs.query_flat, pairs.target_flat, pairs.per_image = out_q, out_t, per_image
+    return pairs
+
+
+class MatchList(list):
+    """the reference's list of per-image (query_index, target_index) tuples, plus the flat device tensors the kernel
+    wrote them into (the concatenations the criterion rebuilds for every loss term)"""
+    query_flat = target_flat = per_image = None
