@@ -369,8 +369,8 @@ def run_ours(args, wl):
                      "frac": achieved / peak, "traffic": load_traffic(dom[0]), "peak_source": peak_src,
                      "note": "achieved = algorithmic bytes of the launch / CUDA-event time on the launch stream; "
                              "bwd includes its cudaMemsetAsync of grad_value"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_max, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "chunks": chunks, "matches_device_path": bool(chk), "pcie": pcie,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_max, "h2d_bytes_per_step": h2d_bytes * world,
+                "d2h_bytes_per_step": d2h_bytes * world, "bytes_note": "whole job (all ranks), like `value`", "chunks": chunks, "matches_device_path": bool(chk), "pcie": pcie,
                 "api": "msda_host_step_f32 (C ABI, pinned host buffers in and out; monosowa_b200.host_step), "
                        f"{args.e2e_images_per_chunk} image(s) per pipeline chunk",
                 "autograd_api_ms_per_step": e2e_autograd_ms,
