@@ -184,6 +184,9 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local_rank)
     import monosowa_b200 as msda
     from monosowa_b200 import workloads as W
+    for kv in filter(None, args.tune.split(",")):
+        k_, v_ = kv.split("=")
+        msda._lib.set_tuning(k_, int(v_))
     use_dist = world > 1
     if use_dist:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # keeps stdout to the one JSON line
@@ -439,6 +442,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--tune", default="", help="A/B only: comma-separated key=value for msda_set_tuning")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     from monosowa_b200 import workloads as W

@@ -169,8 +169,12 @@ long long msda_launch_count(void);     /* kernels this library has launched so f
 
 /* Kernel-selection knobs, for benchmarking A/B runs only (process-wide, not thread-safe
  * against concurrent launches).  Keys: "fwd_variant" / "bwd_variant" (10, 11 = record kernel with
- * work order 0 / 1, 20 = binned backward for any Lq, 99 = generic kernels), "fwd_pipe" / "bwd_pipe" (register-cap / loop flavour of
- * the record kernels, see the launch code).  value -1 restores the measured default.
+ * work order 0 / 1; 20 = binned backward for any Lq, 21 / 23 / 24 = its A/B flavours: grad_out tile in
+ * shared memory / 384-query chunks / loads of two samples issued together; 99 = generic kernels),
+ * "fwd_pipe" / "bwd_pipe" (register-cap / loop flavour of the record kernels, see the launch code; for
+ * the binned backward bwd_pipe = the most samples per query it may bin, e.g. 4 = coarsest level only).
+ * "host_pipe": copy streams per direction of the host-buffer step (1 or 2).
+ * value -1 restores the measured default.
  * Returns MSDA_OK or MSDA_ERR_BAD_SHAPE (unknown key). */
 int msda_set_tuning(const char *key, int value);
 int msda_get_tuning(const char *key);

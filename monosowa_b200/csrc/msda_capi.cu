@@ -144,8 +144,9 @@ constexpr int kHostStages = 3;
 
 struct HostPipe {
     bool ready = false;
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t start = nullptr, done = nullptr, in[kHostStages] = {}, cmp[kHostStages] = {}, out[kHostStages] = {};
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_in2 = nullptr, s_out2 = nullptr;
+    cudaEvent_t start = nullptr, done = nullptr, done2 = nullptr, in[kHostStages] = {}, cmp[kHostStages] = {}, out[kHostStages] = {};
+    cudaEvent_t in2[kHostStages] = {}, out2[kHostStages] = {};
 };
 static HostPipe g_pipe[64];
 static std::mutex g_pipe_mu;
@@ -186,13 +187,17 @@ static int host_pipe(HostPipe **out)
     if (!p.ready) {
         if ((e = cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
         if ((e = cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-        cudaEvent_t *evs[] = {&p.start, &p.done};
+        if ((e = cudaStreamCreateWithFlags(&p.s_in2, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamCreateWithFlags(&p.s_out2, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+        cudaEvent_t *evs[] = {&p.start, &p.done, &p.done2};
         for (cudaEvent_t *ev : evs)
             if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
         for (int i = 0; i < kHostStages; ++i) {
             if ((e = cudaEventCreateWithFlags(&p.in[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
             if ((e = cudaEventCreateWithFlags(&p.cmp[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
             if ((e = cudaEventCreateWithFlags(&p.out[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+            if ((e = cudaEventCreateWithFlags(&p.in2[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+            if ((e = cudaEventCreateWithFlags(&p.out2[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
         }
         p.ready = true;
     }
@@ -230,21 +235,41 @@ static int host_step_impl(const char *fn, DType dt, const void *h_value, const i
     const size_t vb = (size_t)S * M * D * ve, lb = (size_t)Lq * M * L * P * 2 * ce, ab = lb / 2;
     const size_t ob = (size_t)Lq * M * D * ve, gvb = (size_t)S * M * D * ce;
 
+    // One copy stream per direction by default.  host_pipe = 2 splits the four tensors of a chunk over two streams per
+    // direction (to hide the set-up gap of one cudaMemcpyAsync behind the transfer of another): measured SLOWER,
+    // 15.2 vs 14.1 ms per step at configs[1] (profiles/r01b_host_step_streams.jsonl) -- kept as an A/B knob only.
+    const bool dual = tuning().host_pipe == 2;
+    cudaStream_t in_a = p->s_in, in_b = dual ? p->s_in2 : p->s_in, out_a = p->s_out, out_b = dual ? p->s_out2 : p->s_out;
     MSDA_CU(cudaEventRecord(p->start, st));
-    MSDA_CU(cudaStreamWaitEvent(p->s_in, p->start, 0));
-    MSDA_CU(cudaStreamWaitEvent(p->s_out, p->start, 0));
+    MSDA_CU(cudaStreamWaitEvent(in_a, p->start, 0));
+    MSDA_CU(cudaStreamWaitEvent(out_a, p->start, 0));
+    if (dual) {
+        MSDA_CU(cudaStreamWaitEvent(in_b, p->start, 0));
+        MSDA_CU(cudaStreamWaitEvent(out_b, p->start, 0));
+    }
     int chunk = 0;
     for (int n0 = 0; n0 < N; n0 += cb, ++chunk) {
         const int nb = (N - n0 < cb) ? N - n0 : cb;
         const int s = chunk % kHostStages;
         char *base = (char *)workspace + (size_t)s * lay.total;
-        if (chunk >= kHostStages) MSDA_CU(cudaStreamWaitEvent(p->s_in, p->out[s], 0));      // stage drained
-        MSDA_CU(cudaMemcpyAsync(base + lay.value, (const char *)h_value + n0 * vb, nb * vb, cudaMemcpyHostToDevice, p->s_in));
-        MSDA_CU(cudaMemcpyAsync(base + lay.loc, (const char *)h_loc + n0 * lb, nb * lb, cudaMemcpyHostToDevice, p->s_in));
-        MSDA_CU(cudaMemcpyAsync(base + lay.attn, (const char *)h_attn + n0 * ab, nb * ab, cudaMemcpyHostToDevice, p->s_in));
-        MSDA_CU(cudaMemcpyAsync(base + lay.grad_out, (const char *)h_grad_out + n0 * ob, nb * ob, cudaMemcpyHostToDevice, p->s_in));
-        MSDA_CU(cudaEventRecord(p->in[s], p->s_in));
+        if (chunk >= kHostStages) {                                                        // stage drained
+            MSDA_CU(cudaStreamWaitEvent(in_a, p->out[s], 0));
+            if (dual) {
+                MSDA_CU(cudaStreamWaitEvent(in_a, p->out2[s], 0));
+                MSDA_CU(cudaStreamWaitEvent(in_b, p->out[s], 0));
+                MSDA_CU(cudaStreamWaitEvent(in_b, p->out2[s], 0));
+            }
+        }
+        MSDA_CU(cudaMemcpyAsync(base + lay.value, (const char *)h_value + n0 * vb, nb * vb, cudaMemcpyHostToDevice, in_a));
+        MSDA_CU(cudaMemcpyAsync(base + lay.loc, (const char *)h_loc + n0 * lb, nb * lb, cudaMemcpyHostToDevice, in_b));
+        MSDA_CU(cudaMemcpyAsync(base + lay.attn, (const char *)h_attn + n0 * ab, nb * ab, cudaMemcpyHostToDevice, in_a));
+        MSDA_CU(cudaMemcpyAsync(base + lay.grad_out, (const char *)h_grad_out + n0 * ob, nb * ob, cudaMemcpyHostToDevice, in_b));
+        MSDA_CU(cudaEventRecord(p->in[s], in_a));
         MSDA_CU(cudaStreamWaitEvent(st, p->in[s], 0));
+        if (dual) {
+            MSDA_CU(cudaEventRecord(p->in2[s], in_b));
+            MSDA_CU(cudaStreamWaitEvent(st, p->in2[s], 0));
+        }
         Dims dc = c.d;
         dc.N = nb;
         int rc = c.empty_out ? 0 : launch_forward(dt, base + lay.value, shapes, lsi, base + lay.loc, base + lay.attn,
@@ -254,15 +279,21 @@ static int host_step_impl(const char *fn, DType dt, const void *h_value, const i
                              base + lay.gv, base + lay.gl, base + lay.ga, dc, true, st);
         if (rc) return cuda_result(rc, fn);
         MSDA_CU(cudaEventRecord(p->cmp[s], st));
-        MSDA_CU(cudaStreamWaitEvent(p->s_out, p->cmp[s], 0));
-        MSDA_CU(cudaMemcpyAsync((char *)h_out + n0 * ob, base + lay.out, nb * ob, cudaMemcpyDeviceToHost, p->s_out));
-        MSDA_CU(cudaMemcpyAsync((char *)h_gv + n0 * gvb, base + lay.gv, nb * gvb, cudaMemcpyDeviceToHost, p->s_out));
-        MSDA_CU(cudaMemcpyAsync((char *)h_gl + n0 * lb, base + lay.gl, nb * lb, cudaMemcpyDeviceToHost, p->s_out));
-        MSDA_CU(cudaMemcpyAsync((char *)h_ga + n0 * ab, base + lay.ga, nb * ab, cudaMemcpyDeviceToHost, p->s_out));
-        MSDA_CU(cudaEventRecord(p->out[s], p->s_out));
+        MSDA_CU(cudaStreamWaitEvent(out_a, p->cmp[s], 0));
+        if (dual) MSDA_CU(cudaStreamWaitEvent(out_b, p->cmp[s], 0));
+        MSDA_CU(cudaMemcpyAsync((char *)h_out + n0 * ob, base + lay.out, nb * ob, cudaMemcpyDeviceToHost, out_a));
+        MSDA_CU(cudaMemcpyAsync((char *)h_gv + n0 * gvb, base + lay.gv, nb * gvb, cudaMemcpyDeviceToHost, out_b));
+        MSDA_CU(cudaMemcpyAsync((char *)h_gl + n0 * lb, base + lay.gl, nb * lb, cudaMemcpyDeviceToHost, out_a));
+        MSDA_CU(cudaMemcpyAsync((char *)h_ga + n0 * ab, base + lay.ga, nb * ab, cudaMemcpyDeviceToHost, out_b));
+        MSDA_CU(cudaEventRecord(p->out[s], out_a));
+        if (dual) MSDA_CU(cudaEventRecord(p->out2[s], out_b));
     }
-    MSDA_CU(cudaEventRecord(p->done, p->s_out));
+    MSDA_CU(cudaEventRecord(p->done, out_a));
     MSDA_CU(cudaStreamWaitEvent(st, p->done, 0));
+    if (dual) {
+        MSDA_CU(cudaEventRecord(p->done2, out_b));
+        MSDA_CU(cudaStreamWaitEvent(st, p->done2, 0));
+    }
     return cuda_result(0, fn);
 }
 
@@ -360,6 +391,7 @@ static int *tuning_slot(const char *key)
     if (!strcmp(key, "bwd_variant")) return &tuning().bwd_variant;
     if (!strcmp(key, "fwd_pipe")) return &tuning().fwd_pipe;
     if (!strcmp(key, "bwd_pipe")) return &tuning().bwd_pipe;
+    if (!strcmp(key, "host_pipe")) return &tuning().host_pipe;
     return nullptr;
 }
 

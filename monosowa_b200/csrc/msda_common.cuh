@@ -181,6 +181,7 @@ struct Tuning {
     int bwd_variant = -1;
     int fwd_pipe = -1;
     int bwd_pipe = -1;
+    int host_pipe = -1;     // host-buffer step: copy streams per direction (1 or 2)
 };
 Tuning &tuning();
 void count_launch(int n = 1);
