@@ -170,7 +170,8 @@ long long msda_launch_count(void);     /* kernels this library has launched so f
 /* Kernel-selection knobs, for benchmarking A/B runs only (process-wide, not thread-safe
  * against concurrent launches).  Keys: "fwd_variant" / "bwd_variant" (10, 11 = record kernel with
  * work order 0 / 1; 20 = binned backward for any Lq, 21 / 23 / 24 = its A/B flavours: grad_out tile in
- * shared memory / 384-query chunks / loads of two samples issued together; 99 = generic kernels),
+ * shared memory / 384-query chunks / loads of two samples issued together; fwd_variant 30 = forward with the
+ * coarse levels resident in shared memory (measured slower, A/B only); 99 = generic kernels),
  * "fwd_pipe" / "bwd_pipe" (register-cap / loop flavour of the record kernels, see the launch code; for
  * the binned backward bwd_pipe = the most samples per query it may bin, e.g. 4 = coarsest level only).
  * "host_pipe": copy streams per direction of the host-buffer step (1 or 2).

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libmsda_b200.so")
-SOURCES = ["msda_forward.cu", "msda_backward.cu", "msda_backward_binned.cu", "msda_capi.cu"]
+SOURCES = ["msda_forward.cu", "msda_forward_resident.cu", "msda_backward.cu", "msda_backward_binned.cu", "msda_capi.cu"]
 HEADERS = [os.path.join(CSRC, "msda_common.cuh"), os.path.join(CSRC, "msda_records.cuh"), os.path.join(ROOT, "include", "msda_b200.h"),
            os.path.join(ROOT, "include", "monodetr_step_b200.h")]
 # second library: device-side pieces of the MonoDETR training step, kept out of the operator's ABI

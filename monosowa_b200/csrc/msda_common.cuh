@@ -208,6 +208,10 @@ bool binned_backward_applies(const Dims &d, DType dt, bool vec_ok);
 int launch_backward_binned(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
                            const void *attn, const void *grad_out, void *grad_value, void *grad_loc, void *grad_attn,
                            const Dims &d, const void *ref, cudaStream_t st);
+// msda_forward_resident.cu: coarse levels resident in shared memory (long query sets)
+bool resident_forward_applies(const Dims &d, DType dt, bool vec_ok);
+int launch_forward_resident(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                            const void *attn, void *out, const Dims &d, const void *ref, cudaStream_t st);
 const char *forward_kernel_name(DType dt, int D, int L, int P, bool vec_ok);
 const char *backward_kernel_name(DType dt, int D, int L, int P, bool vec_ok);
 

@@ -287,6 +287,7 @@ int launch_forward_fused(DType dt, const void *value, const int64_t *shapes, con
                          const void *offsets, const void *logits, void *out, const Dims &d, cudaStream_t st)
 {
     if ((long)d.S * d.M * d.D >= (1L << 31) || dt == DType::F64) return kUnsupported;
+    if (resident_forward_applies(d, dt, true)) return launch_forward_resident(dt, value, shapes, lsi, offsets, logits, out, d, ref, st);
 #define FUSED_ARGS value, shapes, lsi, ref, offsets, logits, out, d, st
     if (dt == DType::F32) {
         switch (d.D) {
@@ -322,6 +323,7 @@ int launch_forward(DType dt, const void *value, const int64_t *shapes, const int
                    cudaStream_t st)
 {
     if (dt == DType::F64) return run_generic<double, double>(value, shapes, lsi, loc, attn, out, d, st);
+    if (resident_forward_applies(d, dt, vec_ok)) return launch_forward_resident(dt, value, shapes, lsi, loc, attn, out, d, nullptr, st);
     const int rec_order = tuning().fwd_variant == 10 ? 0 : 1;
     if (dt == DType::F32 && use_rec(d, vec_ok)) return dispatch_rec<float>(value, shapes, lsi, loc, attn, out, d, rec_order, st);
     if (dt == DType::BF16 && use_rec(d, vec_ok))

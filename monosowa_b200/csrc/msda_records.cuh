@@ -216,9 +216,12 @@ __device__ __forceinline__ SampleIn fetch_sample_fused(bool has, const float *__
 }
 
 // Build the record of one sample and write it to `rec_off` / `rec_w` (16-byte aligned).  The
-// weights stored are w_ij * a (what both forward and grad_value need).
-__device__ __forceinline__ SampleGeom build_record(uint32_t *rec_off, uint32_t *rec_w, bool has, const SampleIn in,
-                                                   const LevelInfo *s_lv, int l, int xs)
+// weights stored are w_ij * a (what both forward and grad_value need).  The four offsets are
+// (row0 + y * W + x) * stride | tag: for rows in global memory row0 = the level's start index and
+// stride = M * D; a kernel that keeps a level in shared memory passes the level's first shared row, stride = D
+// and a tag bit that tells the consumer where to read (msda_forward_resident.cu).
+__device__ __forceinline__ SampleGeom build_record_at(uint32_t *rec_off, uint32_t *rec_w, bool has, const SampleIn in,
+                                                      const LevelInfo *s_lv, int l, int row0, int stride, int tag)
 {
     SampleGeom gm;
     gm.live = false;
@@ -245,14 +248,21 @@ __device__ __forceinline__ SampleGeom build_record(uint32_t *rec_off, uint32_t *
                        (y1ok && x1ok ? 8u : 0u);
             gm.live = true;
             gm.cell = (t.y0 + 1) * (li.W + 1) + t.x0 + 1;
-            const int r0 = (li.start + y0c * li.W) * xs, r1 = (li.start + y1c * li.W) * xs;
-            off = make_int4(r0 + x0c * xs, r0 + x1c * xs, r1 + x0c * xs, r1 + x1c * xs);
+            const int r0 = (row0 + y0c * li.W) * stride, r1 = (row0 + y1c * li.W) * stride;
+            off = make_int4((r0 + x0c * stride) | tag, (r0 + x1c * stride) | tag, (r1 + x0c * stride) | tag,
+                            (r1 + x1c * stride) | tag);
             wa = make_float4(gm.w00 * a, gm.w01 * a, gm.w10 * a, gm.w11 * a);
         }
     }
     *reinterpret_cast<int4 *>(rec_off) = off;
     *reinterpret_cast<float4 *>(rec_w) = wa;
     return gm;
+}
+
+__device__ __forceinline__ SampleGeom build_record(uint32_t *rec_off, uint32_t *rec_w, bool has, const SampleIn in,
+                                                   const LevelInfo *s_lv, int l, int xs)
+{
+    return build_record_at(rec_off, rec_w, has, in, s_lv, l, has ? s_lv[l].start : 0, xs, 0);
 }
 
 }  // namespace msda

@@ -308,6 +308,39 @@ def test_binned_backward_is_the_default_for_long_query_sets(msda, cuda_device):
     assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and O.rel_l2(a[1], b[1]) < 1e-5
 
 
+# --- resident forward (msda_forward_resident.cu): coarse levels copied into shared memory per CTA ------------
+RES_CASES = [
+    # (shapes, N, M, D, Lq, P)
+    ([(48, 160), (24, 80), (12, 40), (6, 20)], 1, 2, 32, 1300, 4),   # KITTI pyramid: levels 2, 3 resident (77 KB fp32), two chunks
+    ([(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 300, 4),        # every level fits: all gathers from shared memory
+    ([(160, 240), (9, 7)], 1, 2, 32, 200, 4),                        # fine level far too large: only the coarse one resident
+    ([(200, 200)], 1, 1, 32, 100, 4),                                # nothing fits: plain global gathers
+    ([(9, 7), (5, 4), (3, 3)], 2, 4, 16, 1100, 3),                   # D = 16, ragged batches
+    ([(9, 7), (5, 4)], 2, 4, 64, 70, 4),                             # D = 64
+    ([(30, 30), (9, 7), (1, 1)], 2, 3, 32, 1025, 4),                 # one query in the second chunk
+]
+
+
+@pytest.mark.parametrize("case", RES_CASES, ids=lambda c: f"M{c[2]}D{c[3]}Lq{c[4]}P{c[5]}L{len(c[0])}")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_resident_forward_vs_oracle_and_record_kernel(msda, case, dtype):
+    """fwd_variant 30 forces the resident kernel for any Lq: against the fp64 oracle, and bitwise against the record
+    kernel (same arithmetic and accumulation order; only where the rows are read from differs)."""
+    shapes, N, M, D, Lq, P = case
+    value, sh, lsi, loc, attn, grad_out = _random_case(500 + D + Lq, shapes, N, M, D, Lq, P, spread=1.4, shift=-0.2)
+    L = msda._lib
+    try:
+        L.set_tuning("fwd_variant", 30)
+        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=f"resident {case}")
+        b = run_ours(msda, value.to(dtype), sh, lsi, loc.float(), attn.float(), grad_out.to(dtype))
+        L.set_tuning("fwd_variant", 11)
+        L.set_tuning("fwd_pipe", 25)                                   # the compacting record kernel
+        a = run_ours(msda, value.to(dtype), sh, lsi, loc.float(), attn.float(), grad_out.to(dtype))
+    finally:
+        L.set_tuning("fwd_variant", -1); L.set_tuning("fwd_pipe", -1)
+    assert torch.equal(a[0], b[0])
+
+
 def test_edge_locations_exact_borders(msda):
     g = load_golden("op", "d32_edges")
     for dtype in (torch.float64, torch.float32):
@@ -687,12 +720,13 @@ FUSED_CASES = [
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("bwd_variant", [-1, 20])
 def test_fused_preprocessing_matches_unfused_and_oracle(msda, cuda_device, case, dtype, bwd_variant):
-    """bwd_variant 20: the fused flavour of the binned backward (default for Lq >= 1024)"""
+    """bwd_variant 20: the fused flavours of the binned backward and (fwd_variant 30) of the resident forward"""
     msda._lib.set_tuning("bwd_variant", bwd_variant)
+    msda._lib.set_tuning("fwd_variant", 30 if bwd_variant == 20 else -1)
     try:
         _fused_vs_unfused(msda, cuda_device, case, dtype)
     finally:
-        msda._lib.set_tuning("bwd_variant", -1)
+        msda._lib.set_tuning("bwd_variant", -1); msda._lib.set_tuning("fwd_variant", -1)
 
 
 def _fused_vs_unfused(msda, cuda_device, case, dtype):
