@@ -20,10 +20,10 @@
 // Which levels are binned is decided on the device from spatial_shapes (the host never reads them):
 // the coarsest levels while their cells fit kMaxBins, their samples fit kBinSamples per query and the
 // level has at most QC*P pixels (>= 4 updates per row on average).  If none qualifies the kernel is
-// the record kernel plus two block barriers.  Arithmetic: same products as the direct path,
-// ((wy*wx)*a)*g, accumulated per pixel in fp32 before the single global reduction (the reference
-// accumulates all of them with global atomics, ms_deform_im2col_cuda.cuh:125-152) -- covered by the
-// backward tolerance, which already allows for atomic ordering.
+// the record kernel plus one block barrier.  Arithmetic: same products as the direct path,
+// ((wy*wx)*a)*g, accumulated per cell corner in fp32 registers before one global reduction per corner
+// (the reference accumulates every contribution with a global atomic, ms_deform_im2col_cuda.cuh:125-152)
+// -- covered by the backward tolerance, which already allows for atomic ordering.
 #include "msda_common.cuh"
 #include "msda_records.cuh"
 
