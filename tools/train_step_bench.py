@@ -111,6 +111,9 @@ def main():
     ap.add_argument("--host-opt", default="none",
                     help="SURVEY 8 f3: comma list of matcher,ddn,adamw or 'all' -- device-resident replacements of the "
                          "step's host sections (monosowa_b200.step_host); 'none' = the reference's own code")
+    ap.add_argument("--ddp", default="lean", choices=["default", "lean"],
+                    help="lean: static_graph (the unused-parameter search runs once, not every step) and no per-step "
+                         "buffer broadcast (the only buffers are FrozenBatchNorm statistics, which never change)")
     ap.add_argument("--breakdown", action="store_true",
                     help="extra pass: per-phase host issue time vs GPU time (forward / criterion / logging / backward / optimizer)")
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
@@ -169,8 +172,12 @@ def main():
         sum(ld[k] * weight_dict[k] for k in ld if k in weight_dict).backward()
         unused = any(p.requires_grad and p.grad is None for p in model.parameters())
         optimizer.zero_grad()
+        lean = args.ddp == "lean"
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=unused,
-                                                        gradient_as_bucket_view=True)
+                                                        gradient_as_bucket_view=True, static_graph=lean,
+                                                        broadcast_buffers=not lean)
+        if rank == 0:
+            print(f"[ddp] unused parameters: {unused}; mode {args.ddp}", file=sys.stderr)
 
     amp = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.amp == "bf16")
 
@@ -319,7 +326,7 @@ def main():
             "config": {"workload": "BASELINE.json configs[3]: unmodified reference MonoDETR (ResNet-50, 3 enc + 3 dec layers) + "
                                    "SetCriterion + reference AdamW, synthetic KITTI batch", "batch_per_gpu": args.batch,
                        "global_batch": args.batch * world, "image": [384, 1280], "msda_op": args.op, "host_opt": host_opt, "host_opt_check": host_opt_check, "logging": args.logging, "mode": args.mode, "amp": args.amp,
-                       "parallelism": f"ddp{world}", "trainable_params": n_params},
+                       "parallelism": f"ddp{world}", "ddp": args.ddp, "trainable_params": n_params},
             "loss": float(loss), "msda": share, "breakdown": breakdown}), flush=True)
     if world > 1:
         dist.destroy_process_group()
