@@ -125,6 +125,72 @@ def test_foreach_adamw_matches_reference_loop():
         assert torch.allclose(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"], rtol=1e-6, atol=0)
 
 
+# names DeviceMatcher looks up in the matcher's defining module (the reference imports them from utils.box_ops)
+def generalized_box_iou(a, b):
+    raise AssertionError("not reached on CPU tensors")
+
+
+box_cxcylrtb_to_xyxy = generalized_box_iou
+
+
+def test_install_wires_live_objects_and_keeps_the_host_path_for_cpu_tensors():
+    """install() patches instances only; on CPU tensors the matcher keeps the reference's own host path (there is no
+    CPU implementation of the device kernel), and the AdamW replacement is attached only to the reference's class shape"""
+    import types
+    from monosowa_b200 import step_host
+
+    class Matcher(torch.nn.Module):
+        cost_class = cost_bbox = cost_3dcenter = cost_giou = 1.0
+
+        def forward(self, outputs, targets, group_num=11):
+            return "reference-host-path"
+
+    class Balancer(torch.nn.Module):
+        pass
+
+    class DDN(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.balancer = Balancer()
+
+        def build_target_depth_from_3dcenter(self, *a):
+            return "loop"
+
+    class Criterion(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.matcher, self.ddn_loss = Matcher(), DDN()
+
+        def _get_src_permutation_idx(self, indices):
+            return "original"
+
+    class AdamW(torch.optim.Optimizer):
+        def __init__(self, params):
+            super().__init__(params, dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False))
+
+        def step(self):
+            return "loop"
+
+    crit, opt = Criterion(), AdamW([torch.nn.Parameter(torch.zeros(2))])
+    done = step_host.install(crit, opt)
+    assert done == ["matcher", "ddn_loss", "adamw"]
+    outputs = {"pred_boxes": torch.zeros(1, 11, 6), "pred_logits": torch.zeros(1, 11, 3)}
+    assert crit.matcher(outputs, [], group_num=11) == "reference-host-path"
+    assert crit.ddn_loss.build_target_depth_from_3dcenter.__func__ is step_host.paint_depth_targets
+    assert sys.modules[Balancer.__module__].compute_fg_mask is step_host.paint_foreground
+    assert opt.step.__func__ is step_host.foreach_adamw_step
+    assert crit._get_src_permutation_idx([(torch.tensor([1]), torch.tensor([0]))]) == "original"   # plain lists: original code
+    assert step_host.install(crit, torch.optim.AdamW([torch.nn.Parameter(torch.zeros(2))]), matcher=False, ddn=False) == []
+
+
+def test_host_step_rejects_what_it_cannot_run():
+    from monosowa_b200 import host_step
+    v = torch.zeros(1, 4, 2, 32); loc = torch.zeros(1, 3, 2, 1, 4, 2); at = torch.zeros(1, 3, 2, 1, 4); g = torch.zeros(1, 3, 64)
+    sh, lsi = torch.tensor([[2, 2]]), torch.tensor([0])
+    with pytest.raises(NotImplementedError):                # no CUDA tensor anywhere: there is no CPU implementation
+        host_step(v, sh, lsi, loc, at, g)
+
+
 def test_step_library_exports_declared_symbols():
     import ctypes
     import re
