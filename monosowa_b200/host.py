@@ -30,6 +30,11 @@ def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
     return ws
 
 
+def release_workspaces() -> None:
+    """drop the cached device staging buffers (one per device, 3 pipeline stages of images_per_chunk images each)"""
+    _workspaces.clear()
+
+
 def host_step(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, grad_output,
               images_per_chunk: int = 1, results=None, synchronize: bool = True):
     dev = spatial_shapes.device
@@ -62,6 +67,12 @@ def host_step(value, spatial_shapes, level_start_index, sampling_locations, atte
                    torch.empty(sampling_locations.shape, dtype=torch.float32).pin_memory(),
                    torch.empty(attention_weights.shape, dtype=torch.float32).pin_memory())
     out, gv, gl, ga = results
+    for name, t, numel, dt in (("out", out, n * lq * m * d, value.dtype), ("grad_value", gv, value.numel(), torch.float32),
+                               ("grad_loc", gl, sampling_locations.numel(), torch.float32),
+                               ("grad_attn", ga, attention_weights.numel(), torch.float32)):
+        if t.is_cuda or not t.is_contiguous() or t.numel() != numel or t.dtype != dt:
+            raise RuntimeError(f"result buffer {name}: expected a contiguous CPU tensor of {numel} {dt} elements, "
+                               f"got {tuple(t.shape)} {t.dtype} on {t.device}")
     is_bf16 = int(value.dtype == torch.bfloat16)
     need = int(_lib.lib.msda_host_step_workspace_bytes(is_bf16, s, m, d, nl, lq, p, int(images_per_chunk)))
     ws = _workspace(dev, max(need, 256))
