@@ -9,6 +9,12 @@ KITTI-shaped batches, data-parallel with DistributedDataParallel (NCCL) when lau
     torchrun --nproc-per-node 8 tools/train_step_bench.py --steps 50 --warmup 10  # 8 GPUs, 16 img/GPU
     python tools/train_step_bench.py --op ref_cuda      # same model, the reference's own CUDA kernels
                                                         # (oracle/_ref) behind the reference's own ops/ Python
+    python tools/train_step_bench.py --host-opt all     # matcher / DDN targets / AdamW on the device
+                                                        # (monosowa_b200.step_host); prints host_opt_check = loss terms
+                                                        # of the patched vs the reference criterion on the same outputs
+    python tools/train_step_bench.py --breakdown --profile-msda   # per-phase host/GPU times, criterion parts, top kernels
+    ... --ddp default                                   # DDP as constructed by default (lean = static_graph, no buffer
+                                                        # broadcast, is the harness default)
 
 The step mirrors lib/helpers/trainer_helper.py:116-178: zero_grad, forward, SetCriterion, weighted sum,
 reduce_dict + per-key .item() logging (``--logging faithful``; ``lean`` logs every 30th step only),
