@@ -63,7 +63,8 @@ struct BinPlan {
     int binbase[MSDA_MAX_LEVELS];    // first cell of each binned level
 };
 
-template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false, int LDQ = 1, int LOADH = 0>
+template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false, int LDQ = 1, int LOADH = 0,
+          int RUN = 4>
 __global__ void __launch_bounds__(kBinThreads, MINB)
 bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn, const VT *__restrict__ grad_out,
@@ -327,66 +328,89 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     }
     __syncthreads();
 
-    // ---- phase C: one lane group per non-empty base-corner cell ------------------------------------
-    // Every sample of the cell shares its four corner pixels: the group reads each sample's grad_out row
-    // ONCE (a pixel-owner formulation reads it four times -- measured: more L1 data-pipe wavefronts than the
-    // reductions it replaces), forms the four corner rows in registers and sends one REDG line per corner.
+    // ---- phase C: one lane group per run of RUN consecutive base-corner cells -------------------------
+    // Every sample of a cell shares its four corner pixels: the group reads each sample's grad_out row ONCE (a
+    // pixel-owner formulation reads it four times -- measured: more L1 data-pipe wavefronts than the reductions it
+    // replaces) and forms the four corner rows in registers.  Neighbouring cells of a lattice row share a corner
+    // column (the right corners of cell bx are the left corners of cell bx + 1), so a group that walks RUN cells of a
+    // row carries the right accumulators over and sends two REDG lines per cell plus two per run instead of four
+    // per cell: 35 % fewer flush lines at RUN = 4 (bwd_variant 25 = RUN 1 for A/B; the run time is unchanged within
+    // noise, profiles/r01b_sweep_cell_runs.jsonl -- the flush is not what paces the kernel).
     const unsigned gmask = (G == 32) ? kFullMask : (((1u << G) - 1u) << (lane & ~(G - 1)));
     const int nbins = s_plan.nbins, lb = s_plan.lb;
     const float *gq = s_g + gl * kChannelsPerLane;
     const VT *gq_global = grad_out + (((long)n * d.Lq + q0) * d.M + m) * D + gl * kChannelsPerLane;
     for (;;) {
-        int c = 0;
-        if (gl == 0) c = atomicAdd(&s_next, 1);
-        c = __shfl_sync(gmask, c, 0, G);
-        if (c >= nbins) break;
-        const int i0 = hh[c], i1 = hh[c + 1];
-        if (i0 == i1) continue;
-        int l = lb;
-        while (l < d.L - 1 && c < s_plan.binbase[l]) ++l;            // binbase grows towards the finer levels
-        const LevelInfo li = s_lv[l];
-        const int cc = c - s_plan.binbase[l];
-        const int by = cc / (li.W + 1), bx = cc - by * (li.W + 1);
-        const int y0 = by - 1, x0 = bx - 1;
-        float a00[4] = {0.f, 0.f, 0.f, 0.f}, a01[4] = {0.f, 0.f, 0.f, 0.f};
-        float a10[4] = {0.f, 0.f, 0.f, 0.f}, a11[4] = {0.f, 0.f, 0.f, 0.f};
+        int c0 = 0;
+        if (gl == 0) c0 = atomicAdd(&s_next, RUN);
+        c0 = __shfl_sync(gmask, c0, 0, G);
+        if (c0 >= nbins) break;
+        const int c1 = min(c0 + RUN, nbins);
+        float l0[4] = {0.f, 0.f, 0.f, 0.f}, l1[4] = {0.f, 0.f, 0.f, 0.f};      // corners (y0, x0), (y1, x0)
+        float r0[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f};      // corners (y0, x1), (y1, x1)
+        bool lt = false, rt = false;                                           // accumulators hold something
+        for (int c = c0; c < c1; ++c) {
+            int l = lb;
+            while (l < d.L - 1 && c < s_plan.binbase[l]) ++l;        // binbase grows towards the finer levels
+            const LevelInfo li = s_lv[l];
+            const int cc = c - s_plan.binbase[l];
+            const int by = cc / (li.W + 1), bx = cc - by * (li.W + 1);
+            const int i0 = hh[c], i1 = hh[c + 1];
 #pragma unroll 2
-        for (int i = i0; i < i1; ++i) {
-            const int e = s_idx[i];
-            const uint4 en = s_ent[e];
-            float4 gg;
-            if constexpr (GS) {
-                gg = *reinterpret_cast<const float4 *>(gq + (e / kBinSamples) * D);
-            } else {
-                float gt[4];
-                Vec4<VT>::load(gq_global + (long)(e / kBinSamples) * xs, gt);
-                gg = make_float4(gt[0], gt[1], gt[2], gt[3]);
+            for (int i = i0; i < i1; ++i) {
+                const int e = s_idx[i];
+                const uint4 en = s_ent[e];
+                float4 gg;
+                if constexpr (GS) {
+                    gg = *reinterpret_cast<const float4 *>(gq + (e / kBinSamples) * D);
+                } else {
+                    float gt[4];
+                    Vec4<VT>::load(gq_global + (long)(e / kBinSamples) * xs, gt);
+                    gg = make_float4(gt[0], gt[1], gt[2], gt[3]);
+                }
+                const float a = __uint_as_float(en.x), lx = __uint_as_float(en.y), ly = __uint_as_float(en.z);
+                const float hy = 1.f - ly, hx = 1.f - lx;
+                const float w00 = (hy * hx) * a, w01 = (hy * lx) * a, w10 = (ly * hx) * a, w11 = (ly * lx) * a;
+                l0[0] += w00 * gg.x; l0[1] += w00 * gg.y; l0[2] += w00 * gg.z; l0[3] += w00 * gg.w;
+                r0[0] += w01 * gg.x; r0[1] += w01 * gg.y; r0[2] += w01 * gg.z; r0[3] += w01 * gg.w;
+                l1[0] += w10 * gg.x; l1[1] += w10 * gg.y; l1[2] += w10 * gg.z; l1[3] += w10 * gg.w;
+                r1[0] += w11 * gg.x; r1[1] += w11 * gg.y; r1[2] += w11 * gg.z; r1[3] += w11 * gg.w;
             }
-            const float a = __uint_as_float(en.x), lx = __uint_as_float(en.y), ly = __uint_as_float(en.z);
-            const float hy = 1.f - ly, hx = 1.f - lx;
-            const float w00 = (hy * hx) * a, w01 = (hy * lx) * a, w10 = (ly * hx) * a, w11 = (ly * lx) * a;
-            a00[0] += w00 * gg.x; a00[1] += w00 * gg.y; a00[2] += w00 * gg.z; a00[3] += w00 * gg.w;
-            a01[0] += w01 * gg.x; a01[1] += w01 * gg.y; a01[2] += w01 * gg.z; a01[3] += w01 * gg.w;
-            a10[0] += w10 * gg.x; a10[1] += w10 * gg.y; a10[2] += w10 * gg.z; a10[3] += w10 * gg.w;
-            a11[0] += w11 * gg.x; a11[1] += w11 * gg.y; a11[2] += w11 * gg.z; a11[3] += w11 * gg.w;
+            if (i1 > i0) lt = rt = true;
+            // corners outside the map receive nothing (zero padding, ms_deform_im2col_cuda.cuh:125-152)
+            const int y0 = by - 1, x0 = bx - 1;
+            const bool y0ok = y0 >= 0, y1ok = by <= li.H - 1;
+            float *row = gvimg + (li.start + y0 * li.W + x0) * xs;             // pixel (y0, x0)
+            const int ys = li.W * xs;
+            if (lt && x0 >= 0) {                                               // the left column is complete now
+                if (y0ok) red_add_f32x4(row, l0[0], l0[1], l0[2], l0[3]);
+                if (y1ok) red_add_f32x4(row + ys, l1[0], l1[1], l1[2], l1[3]);
+            }
+            if (c + 1 < c1 && bx < li.W) {                                     // next cell continues this lattice row
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) { l0[k2] = r0[k2]; l1[k2] = r1[k2]; r0[k2] = 0.f; r1[k2] = 0.f; }
+                lt = rt;
+                rt = false;
+            } else {
+                if (rt && bx <= li.W - 1) {
+                    if (y0ok) red_add_f32x4(row + xs, r0[0], r0[1], r0[2], r0[3]);
+                    if (y1ok) red_add_f32x4(row + ys + xs, r1[0], r1[1], r1[2], r1[3]);
+                }
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) l0[k2] = l1[k2] = r0[k2] = r1[k2] = 0.f;
+                lt = rt = false;
+            }
         }
-        // corners outside the map receive nothing (zero padding, ms_deform_im2col_cuda.cuh:125-152)
-        const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= li.H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= li.W - 1;
-        float *row = gvimg + (li.start + y0 * li.W + x0) * xs;
-        const int ys = li.W * xs;
-        if (y0ok && x0ok) red_add_f32x4(row, a00[0], a00[1], a00[2], a00[3]);
-        if (y0ok && x1ok) red_add_f32x4(row + xs, a01[0], a01[1], a01[2], a01[3]);
-        if (y1ok && x0ok) red_add_f32x4(row + ys, a10[0], a10[1], a10[2], a10[3]);
-        if (y1ok && x1ok) red_add_f32x4(row + ys + xs, a11[0], a11[1], a11[2], a11[3]);
     }
 }
 
-template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false, int LDQ = 1, int LOADH = 0>
+template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false, int LDQ = 1, int LOADH = 0,
+          int RUN = 4>
 int run_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
             const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, cudaStream_t st)
 {
     using C = BinCfg<D, QCQ, GS>;
-    auto kern = bwd_bin_kernel<VT, D, FUSED, QCQ, MINB, GS, LDQ, LOADH>;
+    auto kern = bwd_bin_kernel<VT, D, FUSED, QCQ, MINB, GS, LDQ, LOADH, RUN>;
     static bool prepared[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -423,6 +447,7 @@ int dispatch_bin(const void *value, const int64_t *shapes, const int64_t *lsi, c
             case 21: return run_bin<VT, 32, FUSED, 256, 3, true>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
             case 23: return run_bin<VT, 32, FUSED, 384, 3, false>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
             case 24: return run_bin<VT, 32, FUSED, 256, 3, false, 2>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+            case 25: return run_bin<VT, 32, FUSED, 256, 3, false, 1, 0, 1>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
             }
         }
         return run_bin<VT, 32, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
@@ -439,7 +464,7 @@ bool binned_backward_applies(const Dims &d, DType dt, bool vec_ok)
     const int v = tuning().bwd_variant;
     if (!vec_ok || dt == DType::F64 || !(d.D == 16 || d.D == 32 || d.D == 64)) return false;
     if ((long)d.S * d.M * d.D >= (1L << 31) || d.L * d.P < 1) return false;
-    if (v == 20 || v == 21 || v == 23 || v == 24) return true;
+    if (v == 20 || v == 21 || (v >= 23 && v <= 25)) return true;
     return v == -1 && d.Lq >= kBinMinQueries;
 }
 

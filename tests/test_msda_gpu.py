@@ -271,7 +271,7 @@ BIN_CASES = [
 
 @pytest.mark.parametrize("case", BIN_CASES, ids=lambda c: f"M{c[2]}D{c[3]}Lq{c[4]}P{c[5]}L{len(c[0])}")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("variant", [20, 21, 23])
+@pytest.mark.parametrize("variant", [20, 21, 23, 25])
 def test_binned_backward_vs_oracle_and_direct(msda, case, dtype, variant):
     """the binned kernel against the fp64 oracle, and against the record kernel: grad_loc / grad_attn come from
     identical arithmetic (bitwise equal), grad_value differs only in summation order."""
