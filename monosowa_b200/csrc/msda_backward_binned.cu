@@ -15,7 +15,8 @@
 //   phase B  exclusive scan of the histogram, then a counting-sort permutation of the entry indices.
 //   phase C  one lane group per non-empty cell: all samples of a cell share their four corner pixels, so the
 //            group reads each sample's grad_out row once (L1/L2 -- phase A just read it), accumulates the four corner
-//            rows ((wy*wx)*a)*g in registers and sends FOUR REDG lines per touched cell per chunk.
+//            rows ((wy*wx)*a)*g in registers and walks runs of consecutive cells, carrying the corner column two
+//            neighbouring cells share: two REDG lines per cell plus two per run.
 //
 // Which levels are binned is decided on the device from spatial_shapes (the host never reads them):
 // the coarsest levels while their cells fit kMaxBins, their samples fit kBinSamples per query and the
