@@ -11,7 +11,7 @@
 //     butterfly reduce-scatter over the lane group (warp shuffles only) and every element is written
 //     exactly once -- no block barriers, no zero-fill (the reference: smem staging, 2 __syncthreads
 //     and a serial D-way sum per sample point).
-// The bound is the SM->L2 reduction port.
+// The bound is the rate at which L2 absorbs reductions, ~49 G 128-byte lines per second chip-wide.
 #include "msda_common.cuh"
 #include "msda_records.cuh"
 
@@ -124,7 +124,7 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 }
                 // a zero weight contributes nothing to grad_value (corner outside the map, sample outside
                 // the window, a == 0, or an exactly integral coordinate): skip the reduction -- the
-                // SM->L2 reduction port is the scarce resource of this kernel
+                // reduction throughput of L2 is the scarce resource of this kernel
                 if (wa.x != 0.f) red_add_f32x4(gvimg + off.x, wa.x * g[0], wa.x * g[1], wa.x * g[2], wa.x * g[3]);
                 if (wa.y != 0.f) red_add_f32x4(gvimg + off.y, wa.y * g[0], wa.y * g[1], wa.y * g[2], wa.y * g[3]);
                 if (wa.z != 0.f) red_add_f32x4(gvimg + off.z, wa.z * g[0], wa.z * g[1], wa.z * g[2], wa.z * g[3]);
