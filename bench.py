@@ -366,8 +366,8 @@ def run_ours(args, wl):
         "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
         "fwd_GBps": ab["fwd"] / (fwd_ms * 1e-3) / 1e9, "bwd_GBps": ab["bwd"] / (bwd_ms * 1e-3) / 1e9,
         "algorithmic_bytes": {"fwd": ab["fwd"], "bwd": ab["bwd"], "gather_cache_level": ab["gather"]},
-        "kernels": {"fwd": msda._lib.lib.msda_describe_forward(32, 0, wl.head_dim, wl.L, wl.points).decode(),
-                    "bwd": msda._lib.lib.msda_describe_backward_lq(32, 0, wl.head_dim, wl.L, wl.points, wl.Lq).decode()},
+        "kernels": {"fwd": msda._lib.describe("forward", wl.dtype, wl.batch, wl.heads, wl.head_dim, wl.L, wl.points, wl.Lq),
+                    "bwd": msda._lib.describe("backward", wl.dtype, wl.batch, wl.heads, wl.head_dim, wl.L, wl.points, wl.Lq)},
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": load_traffic(dom[0]), "peak_source": peak_src,
                      "note": "achieved = algorithmic bytes of the launch / CUDA-event time on the launch stream; "

@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 1
+#define MSDA_ABI_VERSION 2
 #define MSDA_MAX_LEVELS 16
 
 enum {
@@ -87,10 +87,13 @@ int msda_backward_f64(const void *value, const int64_t *spatial_shapes,
                       void *grad_value, void *grad_loc, void *grad_attn,
                       int N, int S, int M, int D, int L, int Lq, int P, void *stream);
 
-/* ---- bf16: value / out / grad_out are bfloat16; sampling_loc, attn_weight, grad_loc and
- *      grad_attn stay float (bf16 cannot hold sub-pixel coordinates); arithmetic is fp32.
- *      grad_value_f32 is a FLOAT accumulation buffer shaped like value (zero-filled here);
- *      the caller narrows it to bf16 once the scatter is complete. ------------------------ */
+/* ---- bf16: value / out / grad_out / grad_value are bfloat16; sampling_loc, attn_weight, grad_loc
+ *      and grad_attn stay float (bf16 cannot hold sub-pixel coordinates); arithmetic is fp32.
+ *      The backward writes the bf16 gradient itself.  Short query sets scatter straight into it
+ *      (REDG.E.ADD.BF16x4: a row receives a handful of additions); long query sets and odd shapes
+ *      accumulate in fp32 and narrow once -- those need `scratch_f32`, a caller-owned DEVICE buffer of
+ *      msda_backward_bf16_scratch_bytes(...) bytes (0 = not needed, pass NULL).
+ *      `pointers_aligned16`: whether every tensor pointer of the call is 16-byte aligned. ---------- */
 int msda_forward_bf16(const void *value, const int64_t *spatial_shapes,
                       const int64_t *level_start_index, const void *sampling_loc,
                       const void *attn_weight, void *out,
@@ -99,44 +102,51 @@ int msda_forward_bf16(const void *value, const int64_t *spatial_shapes,
 int msda_backward_bf16(const void *value, const int64_t *spatial_shapes,
                        const int64_t *level_start_index, const void *sampling_loc,
                        const void *attn_weight, const void *grad_out,
-                       void *grad_value_f32, void *grad_loc, void *grad_attn,
+                       void *grad_value, void *grad_loc, void *grad_attn, void *scratch_f32,
                        int N, int S, int M, int D, int L, int Lq, int P, void *stream);
+size_t msda_backward_bf16_scratch_bytes(int N, int S, int M, int D, int L, int Lq, int P,
+                                        int pointers_aligned16);
 
 /* ---- fused pre-processing -----------------------------------------
  * Same op, but the kernels consume the RAW outputs of the module's two Linears and build the
  * sampling locations and softmax weights in registers -- what the reference module does in PyTorch
- * at ops/modules/ms_deform_attn.py:145-151 for 2-dim reference points:
- *     attn = softmax(attn_logits over L*P);   loc = reference_points[l] + sampling_offsets / (W_l, H_l)
- *   reference_points [N, Lq, L, 2] float (not differentiated here), sampling_offsets [N, Lq, M, L, P, 2]
- *   float, attn_logits [N, Lq, M, L*P] float; value / out / grad_out float or bf16 as above.
- *   backward writes grad_value (fp32 accumulator, zero-filled here), grad_offsets, grad_logits.
+ * at ops/modules/ms_deform_attn.py:145-155:
+ *     attn = softmax(attn_logits over L*P)
+ *     ref_dim 2:  loc = reference_points[l] + sampling_offsets / (W_l, H_l)                   (:149-152)
+ *     ref_dim 6:  loc = ref[l][:2] + sampling_offsets / P * (ref[l][2]+ref[l][3], ref[l][4]+ref[l][5]) * 0.5
+ *                                                                                             (:153-155)
+ *   reference_points [N, Lq, L, ref_dim] float (not differentiated here: d loc / d ref[:2] = 1, so the
+ *   Python layer sums grad_offsets when a caller needs it), sampling_offsets [N, Lq, M, L, P, 2] float,
+ *   attn_logits [N, Lq, M, L*P] float; value / out / grad_out / grad_value float or bf16 as above.
+ *   backward writes grad_value (zero-filled here), grad_offsets, grad_logits; the bf16 flavour takes
+ *   the same `scratch_f32` as msda_backward_bf16.
  * Supported: D in {16, 32, 64}, L*P <= D, 16-byte aligned pointers; otherwise MSDA_ERR_UNSUPPORTED
  * is returned and nothing is launched (callers fall back to the unfused entry points). */
 int msda_forward_fused_f32(const void *value, const int64_t *spatial_shapes,
-                           const int64_t *level_start_index, const void *reference_points,
+                           const int64_t *level_start_index, const void *reference_points, int ref_dim,
                            const void *sampling_offsets, const void *attn_logits, void *out,
                            int N, int S, int M, int D, int L, int Lq, int P, void *stream);
 int msda_forward_fused_bf16(const void *value, const int64_t *spatial_shapes,
-                            const int64_t *level_start_index, const void *reference_points,
+                            const int64_t *level_start_index, const void *reference_points, int ref_dim,
                             const void *sampling_offsets, const void *attn_logits, void *out,
                             int N, int S, int M, int D, int L, int Lq, int P, void *stream);
 int msda_backward_fused_f32(const void *value, const int64_t *spatial_shapes,
-                            const int64_t *level_start_index, const void *reference_points,
+                            const int64_t *level_start_index, const void *reference_points, int ref_dim,
                             const void *sampling_offsets, const void *attn_logits,
                             const void *grad_out, void *grad_value, void *grad_offsets,
                             void *grad_logits, int N, int S, int M, int D, int L, int Lq, int P,
                             void *stream);
 int msda_backward_fused_bf16(const void *value, const int64_t *spatial_shapes,
-                             const int64_t *level_start_index, const void *reference_points,
+                             const int64_t *level_start_index, const void *reference_points, int ref_dim,
                              const void *sampling_offsets, const void *attn_logits,
-                             const void *grad_out, void *grad_value_f32, void *grad_offsets,
-                             void *grad_logits, int N, int S, int M, int D, int L, int Lq, int P,
-                             void *stream);
+                             const void *grad_out, void *grad_value, void *grad_offsets,
+                             void *grad_logits, void *scratch_f32, int N, int S, int M, int D, int L, int Lq,
+                             int P, void *stream);
 
 /* ---- host-buffer step --------------------------------------------------------------------------
  * One forward + backward of a whole batch whose tensors live in HOST memory (pinned memory for
  * asynchronous copies): value / sampling_loc / attn_weight / grad_out in, out / grad_value /
- * grad_loc / grad_attn back, all with the layouts above (grad_value is fp32 for the bf16 flavour, as
+ * grad_loc / grad_attn back, all with the layouts above (grad_value is bf16 for the bf16 flavour, as
  * in msda_backward_bf16).  spatial_shapes and level_start_index stay DEVICE pointers.  The reference
  * has no counterpart: its extension takes CUDA tensors only (ops/src/ms_deform_attn.h:29-38), so a
  * caller with host data pays cudaMemcpy + kernels + cudaMemcpy serially.  Here the batch is pipelined
@@ -144,8 +154,10 @@ int msda_backward_fused_bf16(const void *value, const int64_t *spatial_shapes,
  * streams and `stream`: H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap.
  *   workspace : DEVICE scratch of at least msda_host_step_workspace_bytes(...) bytes, 256-byte
  *               aligned, owned by the caller (the library never allocates device memory).
- * Nothing blocks the host; results are valid once `stream` has been synchronised.  Calls on one
- * device are serialised by a mutex (they share the copy streams). */
+ * Nothing blocks the host; results are valid once `stream` has been synchronised.  The copy streams
+ * are per device: calls on one device are serialised by that device's mutex and each call waits for the
+ * previous call's last copy, so calls from different caller streams need SEPARATE workspaces only if they
+ * are meant to overlap -- they never corrupt each other. */
 int msda_host_step_f32(const void *h_value, const int64_t *spatial_shapes,
                        const int64_t *level_start_index, const void *h_sampling_loc,
                        const void *h_attn_weight, const void *h_grad_out, void *h_out,
@@ -155,7 +167,7 @@ int msda_host_step_f32(const void *h_value, const int64_t *spatial_shapes,
 int msda_host_step_bf16(const void *h_value, const int64_t *spatial_shapes,
                         const int64_t *level_start_index, const void *h_sampling_loc,
                         const void *h_attn_weight, const void *h_grad_out, void *h_out,
-                        void *h_grad_value_f32, void *h_grad_loc, void *h_grad_attn, void *workspace,
+                        void *h_grad_value, void *h_grad_loc, void *h_grad_attn, void *workspace,
                         size_t workspace_bytes, int N, int S, int M, int D, int L, int Lq, int P,
                         int images_per_chunk, void *stream);
 size_t msda_host_step_workspace_bytes(int is_bf16, int S, int M, int D, int L, int Lq, int P,
@@ -167,26 +179,21 @@ const char *msda_build_info(void);     /* "sm_100a nvcc <ver> <date>"           
 const char *msda_last_error(void);     /* thread-local; "" when the last call succeeded      */
 long long msda_launch_count(void);     /* kernels this library has launched so far (memsets excluded) */
 
-/* Kernel-selection knobs, for benchmarking A/B runs only (process-wide, not thread-safe
- * against concurrent launches).  Keys: "fwd_variant" / "bwd_variant" (10, 11 = record kernel with
- * work order 0 / 1; 20 = binned backward for any Lq, 21 / 23 / 24 = its A/B flavours: grad_out tile in
- * shared memory / 384-query chunks / loads of two samples issued together; fwd_variant 30 = forward with the
- * coarse levels resident in shared memory (measured slower, A/B only); 99 = generic kernels),
- * "fwd_pipe" / "bwd_pipe" (register-cap / loop flavour of the record kernels, see the launch code; for
- * the binned backward bwd_pipe = the most samples per query it may bin, e.g. 4 = coarsest level only).
- * "host_pipe": copy streams per direction of the host-buffer step (1 or 2).
- * value -1 restores the measured default.
+/* Kernel-selection knobs, for benchmarking A/B runs and tests only (process-wide, not thread-safe
+ * against concurrent launches).  Keys: "fwd_variant" (11 = record kernel, 99 = generic kernel;
+ * 12 = tile kernel, -DMSDA_AB builds only), "bwd_variant" (11 = record kernel for any Lq, 21 = binned
+ * kernel for any Lq, 99 = generic kernel; 20 = tile kernel, -DMSDA_AB builds only), "fwd_pipe" /
+ * "bwd_pipe" (launch flavours of the -DMSDA_AB kernels; ignored by the shipped library).  value -1 restores the default.
  * Returns MSDA_OK or MSDA_ERR_BAD_SHAPE (unknown key). */
 int msda_set_tuning(const char *key, int value);
 int msda_get_tuning(const char *key);
 
 /* Name of the kernel family the current heuristics pick for this problem: "fwd_rec_f32",
- * "bwd_rec_bf16", "fwd_generic_f64", ... (static storage; for logs, tests and bench.py). */
-const char *msda_describe_forward(int dtype_bits, int is_bf16, int D, int L, int P);
-const char *msda_describe_backward(int dtype_bits, int is_bf16, int D, int L, int P);
-/* The backward choice also depends on the number of queries: long query sets (Lq >= 1024) take the
- * binned kernel ("bwd_bin_f32" / "bwd_bin_bf16": coarse-level grad_value combined in shared memory). */
-const char *msda_describe_backward_lq(int dtype_bits, int is_bf16, int D, int L, int P, int Lq);
+ * "bwd_bin_bf16", "fwd_generic_f64", ... (static storage; for logs, tests and bench.py).  Long query
+ * sets (Lq >= 1024) with enough (image, head, chunk) work items take the binned backward, which combines
+ * the coarse levels' grad_value contributions in shared memory. */
+const char *msda_describe_forward(int dtype_bits, int is_bf16, int N, int M, int D, int L, int P, int Lq);
+const char *msda_describe_backward(int dtype_bits, int is_bf16, int N, int M, int D, int L, int P, int Lq);
 
 #ifdef __cplusplus
 }

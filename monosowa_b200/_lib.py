@@ -10,20 +10,25 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libmsda_b200.so")
+if os.environ.get("MSDA_AB") == "1":                     # measurement build with the A/B launch flavours (build.py --ab)
+    LIB_PATH = os.path.join(_PKG, "libmsda_b200_ab.so")
 
 _vp, _i64p, _int = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int
 _FWD = [_vp, _i64p, _i64p, _vp, _vp, _vp] + [_int] * 7 + [_vp]
 _BWD = [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]
-_FFWD = [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]
-_FBWD = [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]
+_BWD_BF16 = [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]       # + scratch_f32
+_FFWD = [_vp, _i64p, _i64p, _vp, _int, _vp, _vp, _vp] + [_int] * 7 + [_vp]                     # ref, ref_dim, ...
+_FBWD = [_vp, _i64p, _i64p, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]
+_FBWD_BF16 = [_vp, _i64p, _i64p, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp]   # + scratch_f32
 
 _HOST = [_vp] * 11 + [ctypes.c_size_t] + [_int] * 8 + [_vp]
 
 EXPORTS = {
     "msda_forward_f32": (_int, _FWD), "msda_forward_f64": (_int, _FWD), "msda_forward_bf16": (_int, _FWD),
-    "msda_backward_f32": (_int, _BWD), "msda_backward_f64": (_int, _BWD), "msda_backward_bf16": (_int, _BWD),
+    "msda_backward_f32": (_int, _BWD), "msda_backward_f64": (_int, _BWD), "msda_backward_bf16": (_int, _BWD_BF16),
+    "msda_backward_bf16_scratch_bytes": (ctypes.c_size_t, [_int] * 8),
     "msda_forward_fused_f32": (_int, _FFWD), "msda_forward_fused_bf16": (_int, _FFWD),
-    "msda_backward_fused_f32": (_int, _FBWD), "msda_backward_fused_bf16": (_int, _FBWD),
+    "msda_backward_fused_f32": (_int, _FBWD), "msda_backward_fused_bf16": (_int, _FBWD_BF16),
     "msda_host_step_f32": (_int, _HOST), "msda_host_step_bf16": (_int, _HOST),
     "msda_host_step_workspace_bytes": (ctypes.c_size_t, [_int] * 8),
     "msda_abi_version": (_int, []),
@@ -32,11 +37,10 @@ EXPORTS = {
     "msda_launch_count": (ctypes.c_longlong, []),
     "msda_set_tuning": (_int, [ctypes.c_char_p, _int]),
     "msda_get_tuning": (_int, [ctypes.c_char_p]),
-    "msda_describe_forward": (ctypes.c_char_p, [_int] * 5),
-    "msda_describe_backward": (ctypes.c_char_p, [_int] * 5),
-    "msda_describe_backward_lq": (ctypes.c_char_p, [_int] * 6),
+    "msda_describe_forward": (ctypes.c_char_p, [_int] * 8),
+    "msda_describe_backward": (ctypes.c_char_p, [_int] * 8),
 }
-ABI_VERSION = 1
+ABI_VERSION = 2
 ERR_UNSUPPORTED = -4
 
 
@@ -53,7 +57,7 @@ def _open() -> ctypes.CDLL:
     from . import build as _build
     if not os.path.exists(LIB_PATH):
         try:
-            _build.build()
+            _build.build_ab() if LIB_PATH.endswith("_ab.so") else _build.build()
         except Exception as exc:  # noqa: BLE001
             raise ImportError(
                 f"monosowa_b200: {LIB_PATH} is missing and could not be built ({exc}). "
@@ -96,3 +100,16 @@ def get_tuning(key: str) -> int:
 
 def build_info() -> str:
     return lib.msda_build_info().decode()
+
+
+def describe(direction: str, dtype, N: int, M: int, D: int, L: int, P: int, Lq: int) -> str:
+    """kernel family the library picks: describe("backward", torch.float32, 16, 8, 32, 4, 4, 10200) -> "bwd_bin_f32"."""
+    name = str(dtype)
+    bits, bf = (64, 0) if "64" in name else (32, 1 if "bfloat16" in name else 0)
+    fn = lib.msda_describe_forward if direction == "forward" else lib.msda_describe_backward
+    return fn(bits, bf, N, M, D, L, P, Lq).decode()
+
+
+def has_ab_flavours() -> bool:
+    """True for the measurement build (libmsda_b200_ab.so, MSDA_AB=1): the tile kernels exist there."""
+    return "+AB" in build_info()

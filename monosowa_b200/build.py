@@ -20,8 +20,9 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libmsda_b200.so")
-SOURCES = ["msda_forward.cu", "msda_forward_resident.cu", "msda_backward.cu", "msda_backward_binned.cu", "msda_capi.cu"]
-HEADERS = [os.path.join(CSRC, "msda_common.cuh"), os.path.join(CSRC, "msda_records.cuh"), os.path.join(ROOT, "include", "msda_b200.h"),
+SOURCES = ["msda_forward.cu", "msda_backward.cu", "msda_backward_binned.cu", "msda_backward_tiled.cu", "msda_capi.cu"]
+HEADERS = [os.path.join(CSRC, "msda_common.cuh"), os.path.join(CSRC, "msda_records.cuh"), os.path.join(CSRC, "msda_tiles.cuh"),
+           os.path.join(ROOT, "include", "msda_b200.h"),
            os.path.join(ROOT, "include", "monodetr_step_b200.h")]
 # second library: device-side pieces of the MonoDETR training step, kept out of the operator's ABI
 STEP_LIB = os.path.join(PKG, "libmonodetr_step_b200.so")
@@ -46,11 +47,11 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile(nvcc: str, src: str, verbose: bool) -> str:
-    obj = os.path.join(BUILD, os.path.splitext(src)[0] + ".o")
+def _compile(nvcc: str, src: str, verbose: bool, extra=(), tag="") -> str:
+    obj = os.path.join(BUILD, os.path.splitext(src)[0] + tag + ".o")
     srcp = os.path.join(CSRC, src)
     if _stale(obj, [srcp, *HEADERS, os.path.abspath(__file__)]):
-        cmd = [nvcc, *NVCC_FLAGS, "-c", srcp, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", srcp, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
@@ -61,7 +62,7 @@ def _compile(nvcc: str, src: str, verbose: bool) -> str:
     return obj
 
 
-def _build_one(lib: str, sources, force: bool, verbose: bool) -> str:
+def _build_one(lib: str, sources, force: bool, verbose: bool, extra=(), tag="") -> str:
     srcs = [os.path.join(CSRC, s) for s in sources]
     if not force and not _stale(lib, [*srcs, *HEADERS, os.path.abspath(__file__)]):
         return lib
@@ -69,11 +70,11 @@ def _build_one(lib: str, sources, force: bool, verbose: bool) -> str:
     os.makedirs(BUILD, exist_ok=True)
     if force:
         for s in sources:
-            for f in (os.path.splitext(s)[0] + ".o", os.path.splitext(s)[0] + ".o.log"):
+            for f in (os.path.splitext(s)[0] + tag + ".o", os.path.splitext(s)[0] + tag + ".o.log"):
                 if os.path.exists(os.path.join(BUILD, f)):
                     os.remove(os.path.join(BUILD, f))
     with cf.ThreadPoolExecutor(max_workers=len(sources)) as ex:
-        objs = list(ex.map(lambda s: _compile(nvcc, s, verbose), sources))
+        objs = list(ex.map(lambda s: _compile(nvcc, s, verbose, extra, tag), sources))
     cmd = [nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -91,9 +92,22 @@ def build_step(force: bool = False, verbose: bool = False) -> str:
     return _build_one(STEP_LIB, STEP_SOURCES, force, verbose)
 
 
+AB_LIB = os.path.join(PKG, "libmsda_b200_ab.so")
+
+
+def build_ab(force: bool = False, verbose: bool = False) -> str:
+    """The measurement build: the same sources with -DMSDA_AB, i.e. with the extra launch flavours that
+    msda_set_tuning("fwd_pipe" / "bwd_pipe") selects.  A separate, git-ignored file; the product library never
+    carries them.  Loaded instead of libmsda_b200.so when the environment has MSDA_AB=1 (tools/sweep.py)."""
+    return _build_one(AB_LIB, SOURCES, force, verbose, extra=("-DMSDA_AB",), tag=".ab")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--ab", action="store_true", help="also build libmsda_b200_ab.so (A/B launch flavours)")
     a = ap.parse_args()
     print(build(a.force, a.verbose))
+    if a.ab:
+        print(build_ab(a.force, a.verbose))

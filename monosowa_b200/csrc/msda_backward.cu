@@ -30,15 +30,20 @@ namespace msda {
 // FUSED: `loc` = raw sampling offsets, `attn` = raw logits, `ref` = (N,Lq,L,2)
 // reference points; `grad_loc` receives d/d offsets = grad_loc / (W,H) and `grad_attn` receives
 // d/d logits = a * (grad_a - sum_j a_j grad_a_j)  (softmax backward over the L*P samples).
-template <typename VT, int D, int MINB, bool FUSED = false, int LOADH = 0>
+// GVT: element type of grad_value.  float: REDG.E.ADD.F32x4 lines.  bf16 (short query sets with bf16 values):
+// REDG.E.ADD.BF16x4 straight into the bf16 gradient -- a row receives a handful of contributions there, so the
+// per-addition rounding stays within the bf16 tolerance (tests/test_msda_gpu.py) and neither an fp32 staging
+// buffer nor a narrowing pass is needed.
+template <typename VT, int D, int MINB, bool FUSED = false, typename GVT = float>
 __global__ void __launch_bounds__(256, MINB)
 bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                const float *__restrict__ attn, const VT *__restrict__ grad_out,
-               float *__restrict__ grad_value, float *__restrict__ grad_loc,
+               GVT *__restrict__ grad_value, float *__restrict__ grad_loc,
                float *__restrict__ grad_attn, const Dims d, const int order,
-               const float *__restrict__ ref = nullptr)
+               const float *__restrict__ ref = nullptr, const int ref_dim = 2)
 {
+    constexpr int LOADH = 0;
     constexpr int G = D / kChannelsPerLane;
     using RL = RecordLayout<G>;
     constexpr int QPW = RL::QPW;
@@ -58,7 +63,7 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     const long qm = ((long)w.n * d.Lq + w.q) * d.M + w.m;
     const long img = ((long)w.n * d.S * d.M + w.m) * D + gl * kChannelsPerLane;
     const VT *vimg = value + img;
-    float *gvimg = grad_value + img;
+    GVT *gvimg = grad_value + img;
     const int xs = d.M * D;
     uint32_t *grp = s_rec + (threadIdx.x >> 5) * RL::WARP_WORDS + k * RL::GROUP_WORDS;
 
@@ -76,7 +81,8 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
         const bool has = w.valid && sidx < LP;
         if constexpr (FUSED) {
             const int l = has ? sidx / d.P : 0;
-            const SampleIn r = fetch_sample_fused(has, loc, ref, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l, aw[0]);
+            const SampleIn r = fetch_sample_fused(has, loc, ref, ref_dim, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l,
+                                                  d.P, aw[0]);
             aw[0] = aw[1]; aw[1] = aw[2]; aw[2] = aw[3];
             return r;
         } else {
@@ -89,7 +95,7 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
         const bool has = w.valid && sidx < LP;
         const SampleGeom gm = build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, has && d.S > 0, in, s_lv,
                                            sidx / d.P, xs);
-        const float a_cur = in.a;
+        const float a_cur = in.a, ex_cur = in.ex, ey_cur = in.ey;
         __syncwarp();
         in = fetch(sidx + G);                                                              // next batch, in flight
 
@@ -125,10 +131,10 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 // a zero weight contributes nothing to grad_value (corner outside the map, sample outside
                 // the window, a == 0, or an exactly integral coordinate): skip the reduction -- the
                 // reduction throughput of L2 is the scarce resource of this kernel
-                if (wa.x != 0.f) red_add_f32x4(gvimg + off.x, wa.x * g[0], wa.x * g[1], wa.x * g[2], wa.x * g[3]);
-                if (wa.y != 0.f) red_add_f32x4(gvimg + off.y, wa.y * g[0], wa.y * g[1], wa.y * g[2], wa.y * g[3]);
-                if (wa.z != 0.f) red_add_f32x4(gvimg + off.z, wa.z * g[0], wa.z * g[1], wa.z * g[2], wa.z * g[3]);
-                if (wa.w != 0.f) red_add_f32x4(gvimg + off.w, wa.w * g[0], wa.w * g[1], wa.w * g[2], wa.w * g[3]);
+                if (wa.x != 0.f) red_add_x4(gvimg + off.x, wa.x * g[0], wa.x * g[1], wa.x * g[2], wa.x * g[3]);
+                if (wa.y != 0.f) red_add_x4(gvimg + off.y, wa.y * g[0], wa.y * g[1], wa.y * g[2], wa.y * g[3]);
+                if (wa.z != 0.f) red_add_x4(gvimg + off.z, wa.z * g[0], wa.z * g[1], wa.z * g[2], wa.z * g[3]);
+                if (wa.w != 0.f) red_add_x4(gvimg + off.w, wa.w * g[0], wa.w * g[1], wa.w * g[2], wa.w * g[3]);
             }
             group_reduce_scatter<G, 4 * GH>(t, gl);
             th[h][0] = t[0];
@@ -158,9 +164,10 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
             }
             const long si = qm * LP + sidx;
             if constexpr (FUSED) {
-                // d loc / d offset = 1 / (W, H); outside samples have gx = gy = 0 (Wf = Hf = 0 there)
-                const float ox = gm.live ? __fdiv_rn(gx, gm.Wf) : 0.f, oy = gm.live ? __fdiv_rn(gy, gm.Hf) : 0.f;
-                __stcs(reinterpret_cast<float2 *>(grad_loc + 2 * si), make_float2(ox, oy));
+                // d loc / d offset; outside samples have gx = gy = 0
+                const float2 go = gm.live ? fused_offset_grad(ref_dim, gx, gy, gm.Wf, gm.Hf, ex_cur, ey_cur, d.P)
+                                          : make_float2(0.f, 0.f);
+                __stcs(reinterpret_cast<float2 *>(grad_loc + 2 * si), go);
                 pa[0] = pa[1]; pa[1] = pa[2]; pa[2] = pa[3]; pa[3] = a_cur;       // queue of (a, grad_a), newest last
                 pg[0] = pg[1]; pg[1] = pg[2]; pg[2] = pg[3]; pg[3] = ga;
             } else {
@@ -264,63 +271,67 @@ bwd_generic_kernel(const VT *__restrict__ value, const int64_t *__restrict__ sha
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp32 accumulation buffer -> bf16 gradient (bf16 values whose scatter ran in fp32: the tile kernel, the
+// generic kernel).  One pass, 32 bytes in / 16 bytes out per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+narrow_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, const long n)
+{
+    const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i + 8 <= n) {
+        const float4 a = __ldcs(reinterpret_cast<const float4 *>(src + i));
+        const float4 b = __ldcs(reinterpret_cast<const float4 *>(src + i) + 1);
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+        const __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 o;
+        o.x = *reinterpret_cast<const unsigned *>(&p0); o.y = *reinterpret_cast<const unsigned *>(&p1);
+        o.z = *reinterpret_cast<const unsigned *>(&p2); o.w = *reinterpret_cast<const unsigned *>(&p3);
+        *reinterpret_cast<uint4 *>(dst + i) = o;
+    } else {
+        for (long j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-// bwd_variant: -1 default (record kernel, work order 1); 10/11 record kernel with order 0/1; 99 generic.
+// bwd_variant: -1 default (binned kernel for long query sets, else the record kernel); 11 record kernel always;
+// 20 tile kernel always; 21 binned kernel always; 99 generic.
 bool use_rec(const Dims &d, bool vec_ok)
 {
     return vec_ok && tuning().bwd_variant != 99 && (d.D == 16 || d.D == 32 || d.D == 64) &&
            (long)d.S * d.M * d.D < (1L << 31);
 }
 
-template <typename VT, int D>
-int run_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
-            const void *attn, const void *grad_out, void *gv, void *gl, void *ga, const Dims &d,
+template <typename VT, int D, bool FUSED, typename GVT>
+int run_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
+            const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, int ref_dim,
             cudaStream_t st)
 {
     constexpr int QPW = 32 / (D / kChannelsPerLane);
-    const int threads = 256;                       // s_rec is sized for 8 warps
-    const int order = tuning().bwd_variant == 10 ? 0 : 1;
-    const long grid = grid_for(d, order, QPW, threads);
-    // bwd_pipe = requested minimum CTAs/SM (register cap 64K / (256 * MINB)); trades ILP for TLP
-#define MSDA_BWD_REC(MINB)                                                                                  \
-    bwd_rec_kernel<VT, D, MINB><<<(unsigned)grid, threads, 0, st>>>(                                        \
-        (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,      \
-        (float *)gv, (float *)gl, (float *)ga, d, order)
-    switch (tuning().bwd_pipe) {
-    case 1: MSDA_BWD_REC(1); break;
-    case 2: MSDA_BWD_REC(2); break;
-    case 4: MSDA_BWD_REC(4); break;
-    case 13:
-        bwd_rec_kernel<VT, D, 3, false, 1><<<(unsigned)grid, threads, 0, st>>>(
-            (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,
-            (float *)gv, (float *)gl, (float *)ga, d, order);
-        break;
-    case 23:
-        bwd_rec_kernel<VT, D, 3, false, 2><<<(unsigned)grid, threads, 0, st>>>(
-            (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out,
-            (float *)gv, (float *)gl, (float *)ga, d, order);
-        break;
-    default: if (D <= 32) MSDA_BWD_REC(3); else MSDA_BWD_REC(1); break;
-    }
-#undef MSDA_BWD_REC
+    constexpr int MINB = D <= 32 ? 3 : 1;          // 80 registers, 3 CTAs/SM (profiles/r01b_sweep_binned_flavours.jsonl)
+    const long grid = grid_for(d, 1, QPW, 256);
+    if (grid > 0x7fffffffL) return kUnsupported;
+    bwd_rec_kernel<VT, D, MINB, FUSED, GVT><<<(unsigned)grid, 256, 0, st>>>(
+        (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out, (GVT *)gv,
+        (float *)gl, (float *)ga, d, 1, (const float *)ref, ref_dim);
     count_launch();
     return (int)cudaGetLastError();
 }
 
-template <typename VT>
-int dispatch_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
-                 const void *attn, const void *grad_out, void *gv, void *gl, void *ga, const Dims &d,
+template <typename VT, bool FUSED, typename GVT>
+int dispatch_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
+                 const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, int ref_dim,
                  cudaStream_t st)
 {
     switch (d.D) {
-    case 16: return run_rec<VT, 16>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st);
-    case 32: return run_rec<VT, 32>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st);
-    case 64: return run_rec<VT, 64>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st);
+    case 16: return run_rec<VT, 16, FUSED, GVT>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
+    case 32: return run_rec<VT, 32, FUSED, GVT>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
+    case 64: return run_rec<VT, 64, FUSED, GVT>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
     }
-    return (int)cudaErrorInvalidValue;
+    return kUnsupported;
 }
 
 template <typename VT, typename CT>
@@ -331,6 +342,7 @@ int run_generic(const void *value, const int64_t *shapes, const int64_t *lsi, co
     const long warps = (long)d.N * d.Lq * d.M;
     const int threads = 256;
     const long grid = (warps + (threads / 32) - 1) / (threads / 32);
+    if (grid > 0x7fffffffL) return (int)cudaErrorInvalidConfiguration;
     bwd_generic_kernel<VT, CT><<<(unsigned)grid, threads, 0, st>>>(
         (const VT *)value, shapes, lsi, (const CT *)loc, (const CT *)attn, (const VT *)grad_out,
         (CT *)gv, (CT *)gl, (CT *)ga, d);
@@ -338,93 +350,99 @@ int run_generic(const void *value, const int64_t *shapes, const int64_t *lsi, co
     return (int)cudaGetLastError();
 }
 
-}  // namespace
-
-namespace {
-template <typename VT, int D>
-int run_rec_fused(const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref, const void *offsets,
-                  const void *logits, const void *grad_out, void *gv, void *goff, void *glogit, const Dims &d,
-                  cudaStream_t st)
+int narrow_to_bf16(const void *scratch, void *gv, size_t n, cudaStream_t st)
 {
-    constexpr int G = D / kChannelsPerLane;
-    const long grid = grid_for(d, 1, 32 / G, 256);
-#define MSDA_BWD_FUSED(MINB)                                                                                         \
-    bwd_rec_kernel<VT, D, MINB, true><<<(unsigned)grid, 256, 0, st>>>(                                               \
-        (const VT *)value, shapes, lsi, (const float *)offsets, (const float *)logits, (const VT *)grad_out, (float *)gv, \
-        (float *)goff, (float *)glogit, d, 1, (const float *)ref)
-    if (D > 32) MSDA_BWD_FUSED(1);
-    else if (tuning().bwd_pipe == 2) MSDA_BWD_FUSED(2);
-    else MSDA_BWD_FUSED(3);
-#undef MSDA_BWD_FUSED
+    if (n == 0) return 0;
+    const long grid = (long)((n + 8 * 256 - 1) / (8 * 256));
+    narrow_bf16_kernel<<<(unsigned)grid, 256, 0, st>>>((const float *)scratch, (__nv_bfloat16 *)gv, (long)n);
     count_launch();
     return (int)cudaGetLastError();
 }
+
+// the one backward launcher: `ref` != nullptr selects the fused pre-processing flavour
+int backward_any(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref, int ref_dim,
+                 const void *loc, const void *attn, const void *grad_out, void *gv, void *gl, void *ga, void *scratch,
+                 const Dims &d, bool vec_ok, cudaStream_t st)
+{
+    const bool fused = ref != nullptr;
+    const size_t n_gv = (size_t)d.N * d.S * d.M * d.D;
+    const bool direct_bf16 = dt == DType::BF16 && !backward_needs_scratch(d, dt, vec_ok);
+    if (dt == DType::BF16 && !direct_bf16 && n_gv && !scratch) return kNeedsScratch;
+    void *acc = (dt == DType::BF16 && !direct_bf16) ? scratch : gv;         // where the scatter accumulates
+    const size_t acc_elt = dt == DType::F64 ? 8 : (direct_bf16 ? 2 : 4);
+    if (n_gv) {
+        cudaError_t e = cudaMemsetAsync(acc, 0, acc_elt * n_gv, st);         // ms_deform_attn_cuda.cu:121
+        if (e != cudaSuccess) return (int)e;
+    }
+    int rc = kUnsupported;
+    if ((long)d.N * d.Lq * d.M == 0) {
+        rc = 0;
+    } else if (tiled_backward_applies(d, dt, vec_ok)) {
+        rc = launch_backward_tiled(dt, value, shapes, lsi, loc, attn, grad_out, acc, gl, ga, d, ref, ref_dim, st);
+    } else if (binned_backward_applies(d, dt, vec_ok)) {
+        rc = launch_backward_binned(dt, value, shapes, lsi, loc, attn, grad_out, acc, gl, ga, d, ref, ref_dim, st);
+    } else if (dt != DType::F64 && use_rec(d, vec_ok)) {
+#define ARGS value, shapes, lsi, loc, attn, grad_out, acc, gl, ga, d, ref, ref_dim, st
+        if (dt == DType::F32) rc = fused ? dispatch_rec<float, true, float>(ARGS) : dispatch_rec<float, false, float>(ARGS);
+        else if (direct_bf16) rc = fused ? dispatch_rec<__nv_bfloat16, true, __nv_bfloat16>(ARGS)
+                                         : dispatch_rec<__nv_bfloat16, false, __nv_bfloat16>(ARGS);
+        else rc = fused ? dispatch_rec<__nv_bfloat16, true, float>(ARGS) : dispatch_rec<__nv_bfloat16, false, float>(ARGS);
+#undef ARGS
+    }
+    if (rc == kUnsupported) {                                               // odd D, fp64, misaligned, grid overflow
+        if (fused || direct_bf16) return kUnsupported;
+#define ARGS value, shapes, lsi, loc, attn, grad_out, acc, gl, ga, d, st
+        if (dt == DType::F64) rc = run_generic<double, double>(ARGS);
+        else if (dt == DType::F32) rc = run_generic<float, float>(ARGS);
+        else rc = run_generic<__nv_bfloat16, float>(ARGS);
+#undef ARGS
+    }
+    if (rc == 0 && dt == DType::BF16 && !direct_bf16) rc = narrow_to_bf16(scratch, gv, n_gv, st);
+    return rc;
+}
+
 }  // namespace
 
+// bf16 values: does the scatter need the caller's fp32 accumulation buffer (then narrowed into the bf16
+// gradient by one extra pass), or can it go straight into the bf16 gradient with REDG.E.ADD.BF16x4?
+// Direct only for the record kernel when a row receives a handful of additions: every addition rounds to
+// bf16, k of them cost about 1.1e-3 * sqrt((k + 1) / 2) relative error on top of the final rounding.  The host
+// knows the AVERAGE number of contributions per row, Lq*L*P*4 / S; it must not exceed 4 (MonoDETR's decoder:
+// 3.5 with 550 training queries, 0.3 with 50; the coarsest level then sees ~70 per row, measured rel-L2 of the
+// whole gradient 3e-3 -- tests/test_msda_gpu.py::test_config2_decoder_bf16).  Anything denser accumulates in fp32.
+bool backward_needs_scratch(const Dims &d, DType dt, bool vec_ok)
+{
+    if (dt != DType::BF16) return false;
+    if (tiled_backward_applies(d, dt, vec_ok) || binned_backward_applies(d, dt, vec_ok) || !use_rec(d, vec_ok)) return true;
+    if (grid_for(d, 1, 32 / max(1, d.D / kChannelsPerLane), 256) > 0x7fffffffL) return true;
+    return (long)d.Lq * d.L * d.P * 4 > 4L * d.S;
+}
+
 int launch_backward_fused(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref,
-                          const void *offsets, const void *logits, const void *grad_out, void *gv, void *goff,
-                          void *glogit, const Dims &d, cudaStream_t st)
+                          int ref_dim, const void *offsets, const void *logits, const void *grad_out, void *gv,
+                          void *goff, void *glogit, void *scratch, const Dims &d, cudaStream_t st)
 {
     if ((long)d.S * d.M * d.D >= (1L << 31) || dt == DType::F64) return kUnsupported;
     if (!(d.D == 16 || d.D == 32 || d.D == 64) || d.L * d.P > kMaxBatches * (d.D / kChannelsPerLane)) return kUnsupported;
-    const size_t gv_bytes = 4 * (size_t)d.N * d.S * d.M * d.D;
-    if (gv_bytes) {
-        cudaError_t e = cudaMemsetAsync(gv, 0, gv_bytes, st);
-        if (e != cudaSuccess) return (int)e;
-    }
-    if ((long)d.N * d.Lq * d.M == 0) return 0;
-    if (binned_backward_applies(d, dt, true))
-        return launch_backward_binned(dt, value, shapes, lsi, offsets, logits, grad_out, gv, goff, glogit, d, ref, st);
-#define FUSED_ARGS value, shapes, lsi, ref, offsets, logits, grad_out, gv, goff, glogit, d, st
-    if (dt == DType::F32) {
-        switch (d.D) {
-        case 16: return run_rec_fused<float, 16>(FUSED_ARGS);
-        case 32: return run_rec_fused<float, 32>(FUSED_ARGS);
-        case 64: return run_rec_fused<float, 64>(FUSED_ARGS);
-        }
-    } else {
-        switch (d.D) {
-        case 16: return run_rec_fused<__nv_bfloat16, 16>(FUSED_ARGS);
-        case 32: return run_rec_fused<__nv_bfloat16, 32>(FUSED_ARGS);
-        case 64: return run_rec_fused<__nv_bfloat16, 64>(FUSED_ARGS);
-        }
-    }
-#undef FUSED_ARGS
-    return kUnsupported;
+    if (ref_dim != 2 && ref_dim != 6) return kUnsupported;
+    return backward_any(dt, value, shapes, lsi, ref, ref_dim, offsets, logits, grad_out, gv, goff, glogit, scratch, d, true, st);
 }
 
-const char *backward_kernel_name(DType dt, int D, int L, int P, bool vec_ok)
+const char *backward_kernel_name(DType dt, const Dims &d, bool vec_ok)
 {
-    (void)L;
-    Dims d{1, 1, 1, D, 1, 1, P};
-    switch (dt) {
-    case DType::F64: return "bwd_generic_f64";
-    case DType::F32: return use_rec(d, vec_ok) ? "bwd_rec_f32" : "bwd_generic_f32";
-    case DType::BF16: return use_rec(d, vec_ok) ? "bwd_rec_bf16" : "bwd_generic_bf16";
-    }
-    return "?";
+    if (dt == DType::F64) return "bwd_generic_f64";
+    const bool bf = dt == DType::BF16;
+    if (tiled_backward_applies(d, dt, vec_ok)) return bf ? "bwd_tile_bf16" : "bwd_tile_f32";
+    if (binned_backward_applies(d, dt, vec_ok)) return bf ? "bwd_bin_bf16" : "bwd_bin_f32";
+    if (use_rec(d, vec_ok)) return bf ? "bwd_rec_bf16" : "bwd_rec_f32";
+    return bf ? "bwd_generic_bf16" : "bwd_generic_f32";
 }
 
 int launch_backward(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi,
                     const void *loc, const void *attn, const void *grad_out, void *gv, void *gl,
-                    void *ga, const Dims &d, bool vec_ok, cudaStream_t st)
+                    void *ga, void *scratch, const Dims &d, bool vec_ok, cudaStream_t st)
 {
-    const size_t gv_elt = (dt == DType::F64) ? 8 : 4;
-    const size_t gv_bytes = gv_elt * (size_t)d.N * d.S * d.M * d.D;
-    if (gv_bytes) {
-        cudaError_t e = cudaMemsetAsync(gv, 0, gv_bytes, st);      // ms_deform_attn_cuda.cu:121
-        if (e != cudaSuccess) return (int)e;
-    }
-    if ((long)d.N * d.Lq * d.M == 0) return 0;
-    if (binned_backward_applies(d, dt, vec_ok))
-        return launch_backward_binned(dt, value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, nullptr, st);
-#define ARGS value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, st
-    if (dt == DType::F64) return run_generic<double, double>(ARGS);
-    if (dt == DType::F32 && use_rec(d, vec_ok)) return dispatch_rec<float>(ARGS);
-    if (dt == DType::BF16 && use_rec(d, vec_ok)) return dispatch_rec<__nv_bfloat16>(ARGS);
-    if (dt == DType::F32) return run_generic<float, float>(ARGS);
-    return run_generic<__nv_bfloat16, float>(ARGS);
-#undef ARGS
+    return backward_any(dt, value, shapes, lsi, nullptr, 2, loc, attn, grad_out, gv, gl, ga, scratch, d, vec_ok, st);
 }
 
 }  // namespace msda

@@ -38,7 +38,7 @@ constexpr int kBinThreads = 256;
 constexpr unsigned kNoEntry = 0xffffffffu;
 constexpr int kBinMinQueries = 1024;  // below this the chunks are too few / too short to pay for the two extra phases
 
-template <int D, int QCQ = 0, bool GS = false>
+template <int D, int QCQ = 0>
 struct BinCfg {
     static constexpr int G = D / kChannelsPerLane;
     static constexpr int QPW = 32 / G;
@@ -46,7 +46,7 @@ struct BinCfg {
     static constexpr int QC = QCQ > 0 ? QCQ : (D <= 32 ? 256 : 128);   // queries per CTA
     static constexpr int HIST_HALVES = kMaxBins + 2;              // 16-bit counters, packed two per word
     static constexpr int HIST_WORDS = (HIST_HALVES + 1) / 2;
-    static constexpr int G_BYTES = GS ? QC * D * 4 : 0;          // the chunk's grad_out rows (GS) or re-read from L1/L2
+    static constexpr int G_BYTES = 0;                             // the chunk's grad_out rows are re-read from L1/L2
     static constexpr int ENT_BYTES = QC * kBinSamples * 16;
     static constexpr int HIST_BYTES = ((HIST_WORDS * 4 + 15) / 16) * 16;
     static constexpr int REC_BYTES = (kBinThreads / 32) * RecordLayout<G>::WARP_WORDS * 4;
@@ -64,15 +64,16 @@ struct BinPlan {
     int binbase[MSDA_MAX_LEVELS];    // first cell of each binned level
 };
 
-template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false, int LDQ = 1, int LOADH = 0,
-          int RUN = 4>
+template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3>
 __global__ void __launch_bounds__(kBinThreads, MINB)
 bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn, const VT *__restrict__ grad_out,
                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn,
-               const Dims d, const float *__restrict__ ref, const int max_binned)
+               const Dims d, const float *__restrict__ ref, const int ref_dim, const int max_binned)
 {
-    using C = BinCfg<D, QCQ, GS>;
+    constexpr bool GS = false;
+    constexpr int LDQ = 1, LOADH = 0, RUN = 4;
+    using C = BinCfg<D, QCQ>;
     using RL = RecordLayout<C::G>;
     constexpr int G = C::G, QPW = C::QPW, QPI = C::QPI, QC = C::QC;
     constexpr int LD = (LDQ <= G / 2) ? LDQ : G / 2;     // samples whose loads are issued together
@@ -154,7 +155,8 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
             const bool has = qvalid && sidx < LP;
             if constexpr (FUSED) {
                 const int l = has ? sidx / d.P : 0;
-                const SampleIn r = fetch_sample_fused(has, loc, ref, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l, aw[0]);
+                const SampleIn r = fetch_sample_fused(has, loc, ref, ref_dim, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l,
+                                                      d.P, aw[0]);
                 aw[0] = aw[1]; aw[1] = aw[2]; aw[2] = aw[3];
                 return r;
             } else {
@@ -167,12 +169,12 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
             const bool has = qvalid && sidx < LP;
             const int l = sidx / d.P;
             const SampleGeom gm = build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, has && d.S > 0, in, s_lv, l, xs);
-            const float a_cur = in.a;
+            const float a_cur = in.a, ex_cur = in.ex, ey_cur = in.ey;
             if (has && sidx >= lbP) {
                 // binned level: park the sample instead of sending its four reduction lines to L2
                 uint4 e = make_uint4(0u, 0u, 0u, kNoEntry);
                 if (gm.live && gm.a != 0.f) {
-                    const int bin = s_plan.binbase[l] + gm.cell;
+                    const int bin = s_plan.binbase[l] + gm.cy * (s_lv[l].W + 1) + gm.cx;
                     const unsigned sh = (bin & 1) * 16;
                     const unsigned old = atomicAdd(&s_hist[bin >> 1], 1u << sh);
                     e = make_uint4(__float_as_uint(gm.a), __float_as_uint(gm.lx), __float_as_uint(gm.ly),
@@ -258,8 +260,9 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 }
                 const long si = qm * LP + sidx;
                 if constexpr (FUSED) {
-                    const float ox = gm.live ? __fdiv_rn(gx, gm.Wf) : 0.f, oy = gm.live ? __fdiv_rn(gy, gm.Hf) : 0.f;
-                    __stcs(reinterpret_cast<float2 *>(grad_loc + 2 * si), make_float2(ox, oy));
+                    const float2 go = gm.live ? fused_offset_grad(ref_dim, gx, gy, gm.Wf, gm.Hf, ex_cur, ey_cur, d.P)
+                                              : make_float2(0.f, 0.f);
+                    __stcs(reinterpret_cast<float2 *>(grad_loc + 2 * si), go);
                     pa[0] = pa[1]; pa[1] = pa[2]; pa[2] = pa[3]; pa[3] = a_cur;
                     pg[0] = pg[1]; pg[1] = pg[2]; pg[2] = pg[3]; pg[3] = ga;
                 } else {
@@ -405,13 +408,16 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     }
 }
 
-template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, bool GS = false, int LDQ = 1, int LOADH = 0,
-          int RUN = 4>
+template <typename VT, int D, bool FUSED>
 int run_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
-            const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, cudaStream_t st)
+            const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, int ref_dim, cudaStream_t st)
 {
-    using C = BinCfg<D, QCQ, GS>;
-    auto kern = bwd_bin_kernel<VT, D, FUSED, QCQ, MINB, GS, LDQ, LOADH, RUN>;
+    // chunk size / register cap / where the chunk's grad_out rows live were swept on B200
+    // (profiles/r01b_sweep_binned_flavours*.jsonl): 256 queries at 80 registers (3 CTAs/SM) with grad_out re-read
+    // through L1/L2 in phase C wins -- parking the rows in shared memory (+32 KB per CTA) shrinks L1 to ~28 KB and
+    // costs 3 %; 64 registers (4 CTAs/SM), 128 registers (2 CTAs/SM) and 128/160/320/512-query chunks are 1-10 % slower
+    using C = BinCfg<D>;
+    auto kern = bwd_bin_kernel<VT, D, FUSED>;
     static bool prepared[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -426,61 +432,52 @@ int run_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const 
     if (grid > 0x7fffffffL) return kUnsupported;
     kern<<<(unsigned)grid, kBinThreads, C::SMEM, st>>>((const VT *)value, shapes, lsi, (const float *)loc,
                                                         (const float *)attn, (const VT *)grad_out, (float *)gv,
-                                                        (float *)gl, (float *)ga, d, (const float *)ref,
-                                                        min(kBinSamples, tuning().bwd_pipe > 0 ? tuning().bwd_pipe : kBinSamples));
+                                                        (float *)gl, (float *)ga, d, (const float *)ref, ref_dim, kBinSamples);
     count_launch();
     return (int)cudaGetLastError();
 }
 
 template <typename VT, bool FUSED>
 int dispatch_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
-                 const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, cudaStream_t st)
+                 const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, int ref_dim,
+                 cudaStream_t st)
 {
     switch (d.D) {
-    case 16: return run_bin<VT, 16, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
-    // chunk size / register cap / where the chunk's grad_out rows live were swept on B200
-    // (profiles/r01b_sweep_binned_flavours*.jsonl): 256 queries at 80 registers (3 CTAs/SM) with grad_out re-read
-    // through L1/L2 in phase C wins -- parking the rows in shared memory (GS, +32 KB per CTA) shrinks L1 to ~28 KB and
-    // costs 3 %; 64 registers (4 CTAs/SM), 128 registers (2 CTAs/SM) and 128/160/320/512-query chunks are 1-10 % slower
-    case 32:
-        if constexpr (!FUSED) {                          // A/B flavours kept for the record (see the sweep files)
-            switch (tuning().bwd_variant) {
-            case 21: return run_bin<VT, 32, FUSED, 256, 3, true>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
-            case 23: return run_bin<VT, 32, FUSED, 384, 3, false>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
-            case 24: return run_bin<VT, 32, FUSED, 256, 3, false, 2>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
-            case 25: return run_bin<VT, 32, FUSED, 256, 3, false, 1, 0, 1>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
-            }
-        }
-        return run_bin<VT, 32, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
-    case 64: return run_bin<VT, 64, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+    case 16: return run_bin<VT, 16, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
+    case 32: return run_bin<VT, 32, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
+    case 64: return run_bin<VT, 64, FUSED>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
     }
     return kUnsupported;
 }
 
 }  // namespace
 
-// bwd_variant: -1 default (binned kernel for long query sets); 20 force it for any Lq; 10/11/99 never.
+// bwd_variant: -1 default (binned kernel for long query sets); 21 force it for any Lq; 11/20/99 never.
 bool binned_backward_applies(const Dims &d, DType dt, bool vec_ok)
 {
     const int v = tuning().bwd_variant;
     if (!vec_ok || dt == DType::F64 || !(d.D == 16 || d.D == 32 || d.D == 64)) return false;
     if ((long)d.S * d.M * d.D >= (1L << 31) || d.L * d.P < 1) return false;
-    if (v == 20 || v == 21 || (v >= 23 && v <= 25)) return true;
-    return v == -1 && d.Lq >= kBinMinQueries;
+    if (v == 21) return true;
+    // Three barrier-separated phases per CTA need several waves of CTAs to overlap each other: measured on B200
+    // (profiles/r02_kernel_family_table.jsonl) the binned kernel wins at 5120 and 6400 CTAs (KITTI batch 16, Waymo
+    // batch 4: 1.46 vs 1.53 ms, 2.06 vs 2.09 ms) and loses at ~1400 (KITTI-360 / 640x960 batch 4: 0.47 vs 0.43 ms).
+    const long chunk = d.D <= 32 ? 256 : 128;
+    return v == -1 && d.Lq >= kBinMinQueries && (long)d.N * d.M * ((d.Lq + chunk - 1) / chunk) >= 3072;
 }
 
-// grad_value must already be zero-filled.  `ref` != nullptr selects the fused pre-processing flavour
-// (loc = raw offsets, attn = raw logits).
+// grad_value (fp32) must already be zero-filled.  `ref` != nullptr selects the fused pre-processing flavour
+// (loc = raw offsets, attn = raw logits, ref_dim = 2 or 6).
 int launch_backward_binned(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
                            const void *attn, const void *grad_out, void *gv, void *gl, void *ga, const Dims &d,
-                           const void *ref, cudaStream_t st)
+                           const void *ref, int ref_dim, cudaStream_t st)
 {
     if (ref) {
-        if (dt == DType::F32) return dispatch_bin<float, true>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
-        return dispatch_bin<__nv_bfloat16, true>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, st);
+        if (dt == DType::F32) return dispatch_bin<float, true>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
+        return dispatch_bin<__nv_bfloat16, true>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
     }
-    if (dt == DType::F32) return dispatch_bin<float, false>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, nullptr, st);
-    return dispatch_bin<__nv_bfloat16, false>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, nullptr, st);
+    if (dt == DType::F32) return dispatch_bin<float, false>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, nullptr, 2, st);
+    return dispatch_bin<__nv_bfloat16, false>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, nullptr, 2, st);
 }
 
 }  // namespace msda

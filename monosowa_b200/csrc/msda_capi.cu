@@ -92,7 +92,7 @@ static int forward_impl(const char *fn, DType dt, const void *value, const int64
 
 static int backward_impl(const char *fn, DType dt, const void *value, const int64_t *shapes,
                          const int64_t *lsi, const void *loc, const void *attn, const void *grad_out,
-                         void *gv, void *gl, void *ga, int N, int S, int M, int D, int L, int Lq, int P,
+                         void *gv, void *gl, void *ga, void *scratch, int N, int S, int M, int D, int L, int Lq, int P,
                          void *stream)
 {
     Checked c;
@@ -102,34 +102,47 @@ static int backward_impl(const char *fn, DType dt, const void *value, const int6
     if (has_value && !gv) return fail(MSDA_ERR_NULL_POINTER, "%s: grad_value is NULL", fn);
     if (has_samples && (!gl || !ga)) return fail(MSDA_ERR_NULL_POINTER, "%s: grad_loc / grad_attn is NULL", fn);
     if (!c.empty_out && !grad_out) return fail(MSDA_ERR_NULL_POINTER, "%s: grad_out is NULL", fn);
-    c.vec_ok = c.vec_ok && aligned(grad_out, 16) && aligned(gv, 16) && aligned(gl, 16) && aligned(ga, 16);
-    return cuda_result(
-        launch_backward(dt, value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, c.d, c.vec_ok, (cudaStream_t)stream), fn);
+    c.vec_ok = c.vec_ok && aligned(grad_out, 16) && aligned(gv, 16) && aligned(gl, 16) && aligned(ga, 16) &&
+               aligned(scratch, 16);
+    const int rc = launch_backward(dt, value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, scratch, c.d, c.vec_ok,
+                                   (cudaStream_t)stream);
+    if (rc == kNeedsScratch)
+        return fail(MSDA_ERR_NULL_POINTER, "%s: scratch_f32 is NULL but this shape accumulates in fp32 "
+                    "(msda_backward_bf16_scratch_bytes)", fn);
+    return cuda_result(rc, fn);
 }
 
 static int fused_impl(const char *fn, DType dt, bool backward, const void *value, const int64_t *shapes,
-                      const int64_t *lsi, const void *ref, const void *offsets, const void *logits, const void *grad_out,
-                      void *o0, void *o1, void *o2, int N, int S, int M, int D, int L, int Lq, int P, void *stream)
+                      const int64_t *lsi, const void *ref, int ref_dim, const void *offsets, const void *logits,
+                      const void *grad_out, void *o0, void *o1, void *o2, void *scratch, int N, int S, int M, int D,
+                      int L, int Lq, int P, void *stream)
 {
     Checked c;
     if (int rc = check_common(fn, dt, value, shapes, lsi, offsets, logits, N, S, M, D, L, Lq, P, &c)) return rc;
+    if (ref_dim != 2 && ref_dim != 6)
+        return fail(MSDA_ERR_UNSUPPORTED, "%s: reference points must have 2 or 6 components, got %d", fn, ref_dim);
     const bool has_q = (long long)N * Lq * M > 0;
     if (has_q && L > 0 && !ref) return fail(MSDA_ERR_NULL_POINTER, "%s: reference_points is NULL", fn);
     if (!backward && !c.empty_out && !o0) return fail(MSDA_ERR_NULL_POINTER, "%s: out is NULL", fn);
     if (backward && ((!c.empty_out && !grad_out) || ((long long)N * S * M * D > 0 && !o0) ||
                      ((long long)N * Lq * M * L * P > 0 && (!o1 || !o2))))
         return fail(MSDA_ERR_NULL_POINTER, "%s: a gradient pointer is NULL", fn);
-    const bool al = c.vec_ok && aligned(ref, 8) && aligned(o0, 16) && aligned(o1, 8) && aligned(o2, 4) && aligned(grad_out, 8);
+    const bool al = c.vec_ok && aligned(ref, 8) && aligned(o0, 16) && aligned(o1, 8) && aligned(o2, 4) &&
+                    aligned(grad_out, 8) && aligned(scratch, 16);
     if (!al) return fail(MSDA_ERR_UNSUPPORTED, "%s: pointers are not 16-byte aligned", fn);
     int rc;
     if (!backward) {
         if (c.empty_out) return cuda_result(0, fn);
-        rc = launch_forward_fused(dt, value, shapes, lsi, ref, offsets, logits, o0, c.d, (cudaStream_t)stream);
+        rc = launch_forward_fused(dt, value, shapes, lsi, ref, ref_dim, offsets, logits, o0, c.d, (cudaStream_t)stream);
     } else {
-        rc = launch_backward_fused(dt, value, shapes, lsi, ref, offsets, logits, grad_out, o0, o1, o2, c.d, (cudaStream_t)stream);
+        rc = launch_backward_fused(dt, value, shapes, lsi, ref, ref_dim, offsets, logits, grad_out, o0, o1, o2, scratch, c.d,
+                                   (cudaStream_t)stream);
     }
     if (rc == kUnsupported)
         return fail(MSDA_ERR_UNSUPPORTED, "%s: no fused kernel for D=%d L*P=%d (use the unfused entry points)", fn, D, L * P);
+    if (rc == kNeedsScratch)
+        return fail(MSDA_ERR_NULL_POINTER, "%s: scratch_f32 is NULL but this shape accumulates in fp32 "
+                    "(msda_backward_bf16_scratch_bytes)", fn);
     return cuda_result(rc, fn);
 }
 
@@ -143,18 +156,17 @@ static int fused_impl(const char *fn, DType dt, bool backward, const void *value
 constexpr int kHostStages = 3;
 
 struct HostPipe {
-    bool ready = false;
-    cudaStream_t s_in = nullptr, s_out = nullptr, s_in2 = nullptr, s_out2 = nullptr;
-    cudaEvent_t start = nullptr, done = nullptr, done2 = nullptr, in[kHostStages] = {}, cmp[kHostStages] = {}, out[kHostStages] = {};
-    cudaEvent_t in2[kHostStages] = {}, out2[kHostStages] = {};
+    std::mutex mu;                  // serialises the calls of one device (they share the copy streams)
+    bool ready = false, has_prev = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t start = nullptr, done = nullptr, in[kHostStages] = {}, cmp[kHostStages] = {}, out[kHostStages] = {};
 };
 static HostPipe g_pipe[64];
-static std::mutex g_pipe_mu;
 
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 struct HostStage {
-    size_t value, loc, attn, grad_out, out, gv, gl, ga, total;
+    size_t value, loc, attn, grad_out, out, gv, gl, ga, scratch, total;
 };
 
 static HostStage host_stage_layout(DType dt, const Dims &d, int images)
@@ -162,7 +174,10 @@ static HostStage host_stage_layout(DType dt, const Dims &d, int images)
     const size_t ve = dt == DType::F64 ? 8 : (dt == DType::F32 ? 4 : 2), ce = dt == DType::F64 ? 8 : 4;
     const size_t n = (size_t)images;
     const size_t vb = n * d.S * d.M * d.D * ve, lb = n * d.Lq * d.M * d.L * d.P * 2 * ce, ab = lb / 2;
-    const size_t ob = n * d.Lq * d.M * d.D * ve, gvb = n * d.S * d.M * d.D * ce;
+    const size_t ob = n * d.Lq * d.M * d.D * ve;
+    Dims dc = d;
+    dc.N = images;
+    const size_t sb = backward_needs_scratch(dc, dt, true) ? n * d.S * d.M * d.D * 4 : 0;
     HostStage st;
     size_t o = 0;
     st.value = o; o += align256(vb);
@@ -170,38 +185,49 @@ static HostStage host_stage_layout(DType dt, const Dims &d, int images)
     st.attn = o; o += align256(ab);
     st.grad_out = o; o += align256(ob);
     st.out = o; o += align256(ob);
-    st.gv = o; o += align256(gvb);
+    st.gv = o; o += align256(vb);
     st.gl = o; o += align256(lb);
     st.ga = o; o += align256(ab);
+    st.scratch = o; o += align256(sb);
     st.total = o;
     return st;
 }
 
-static int host_pipe(HostPipe **out)
+static void host_pipe_destroy(HostPipe &p)
 {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return (int)e;
-    if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
-    HostPipe &p = g_pipe[dev];
-    if (!p.ready) {
-        if ((e = cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-        if ((e = cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-        if ((e = cudaStreamCreateWithFlags(&p.s_in2, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-        if ((e = cudaStreamCreateWithFlags(&p.s_out2, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-        cudaEvent_t *evs[] = {&p.start, &p.done, &p.done2};
-        for (cudaEvent_t *ev : evs)
-            if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-        for (int i = 0; i < kHostStages; ++i) {
-            if ((e = cudaEventCreateWithFlags(&p.in[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-            if ((e = cudaEventCreateWithFlags(&p.cmp[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-            if ((e = cudaEventCreateWithFlags(&p.out[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-            if ((e = cudaEventCreateWithFlags(&p.in2[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-            if ((e = cudaEventCreateWithFlags(&p.out2[i], cudaEventDisableTiming)) != cudaSuccess) return (int)e;
-        }
-        p.ready = true;
+    if (p.s_in) cudaStreamDestroy(p.s_in);
+    if (p.s_out) cudaStreamDestroy(p.s_out);
+    if (p.start) cudaEventDestroy(p.start);
+    if (p.done) cudaEventDestroy(p.done);
+    for (int i = 0; i < kHostStages; ++i) {
+        if (p.in[i]) cudaEventDestroy(p.in[i]);
+        if (p.cmp[i]) cudaEventDestroy(p.cmp[i]);
+        if (p.out[i]) cudaEventDestroy(p.out[i]);
+        p.in[i] = p.cmp[i] = p.out[i] = nullptr;
     }
-    *out = &p;
+    p.s_in = p.s_out = nullptr;
+    p.start = p.done = nullptr;
+    p.ready = p.has_prev = false;
+}
+
+// called with p.mu held
+static int host_pipe_prepare(HostPipe &p)
+{
+    if (p.ready) return 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming);
+    for (int i = 0; i < kHostStages && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&p.in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.cmp[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.out[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        host_pipe_destroy(p);               // nothing half-built survives a failed attempt
+        return (int)e;
+    }
+    p.ready = true;
     return 0;
 }
 
@@ -227,73 +253,54 @@ static int host_step_impl(const char *fn, DType dt, const void *h_value, const i
     if (workspace_bytes < (size_t)kHostStages * lay.total || !aligned(workspace, 256))
         return fail(MSDA_ERR_BAD_SHAPE, "%s: workspace too small or not 256-byte aligned (%zu bytes needed)", fn,
                     (size_t)kHostStages * lay.total);
-    std::lock_guard<std::mutex> lock(g_pipe_mu);
-    HostPipe *p = nullptr;
-    if (int rc = host_pipe(&p)) return cuda_result(rc, fn);
+    int dev = 0;
+    MSDA_CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return cuda_result((int)cudaErrorInvalidDevice, fn);
+    HostPipe &p = g_pipe[dev];
+    std::lock_guard<std::mutex> lock(p.mu);
+    if (int rc = host_pipe_prepare(p)) return cuda_result(rc, fn);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t ve = dt == DType::F64 ? 8 : (dt == DType::F32 ? 4 : 2), ce = dt == DType::F64 ? 8 : 4;
     const size_t vb = (size_t)S * M * D * ve, lb = (size_t)Lq * M * L * P * 2 * ce, ab = lb / 2;
-    const size_t ob = (size_t)Lq * M * D * ve, gvb = (size_t)S * M * D * ce;
+    const size_t ob = (size_t)Lq * M * D * ve;
 
-    // One copy stream per direction by default.  host_pipe = 2 splits the four tensors of a chunk over two streams per
-    // direction (to hide the set-up gap of one cudaMemcpyAsync behind the transfer of another): measured SLOWER,
-    // 15.2 vs 14.1 ms per step at configs[1] (profiles/r01b_host_step_streams.jsonl) -- kept as an A/B knob only.
-    const bool dual = tuning().host_pipe == 2;
-    cudaStream_t in_a = p->s_in, in_b = dual ? p->s_in2 : p->s_in, out_a = p->s_out, out_b = dual ? p->s_out2 : p->s_out;
-    MSDA_CU(cudaEventRecord(p->start, st));
-    MSDA_CU(cudaStreamWaitEvent(in_a, p->start, 0));
-    MSDA_CU(cudaStreamWaitEvent(out_a, p->start, 0));
-    if (dual) {
-        MSDA_CU(cudaStreamWaitEvent(in_b, p->start, 0));
-        MSDA_CU(cudaStreamWaitEvent(out_b, p->start, 0));
-    }
+    MSDA_CU(cudaEventRecord(p.start, st));
+    MSDA_CU(cudaStreamWaitEvent(p.s_in, p.start, 0));
+    MSDA_CU(cudaStreamWaitEvent(p.s_out, p.start, 0));
+    // the previous call on this device (possibly from another caller stream) may still be computing in or copying
+    // out of the stages this call is about to overwrite: its last D2H is behind all of that
+    if (p.has_prev) MSDA_CU(cudaStreamWaitEvent(p.s_in, p.done, 0));
     int chunk = 0;
     for (int n0 = 0; n0 < N; n0 += cb, ++chunk) {
         const int nb = (N - n0 < cb) ? N - n0 : cb;
         const int s = chunk % kHostStages;
         char *base = (char *)workspace + (size_t)s * lay.total;
-        if (chunk >= kHostStages) {                                                        // stage drained
-            MSDA_CU(cudaStreamWaitEvent(in_a, p->out[s], 0));
-            if (dual) {
-                MSDA_CU(cudaStreamWaitEvent(in_a, p->out2[s], 0));
-                MSDA_CU(cudaStreamWaitEvent(in_b, p->out[s], 0));
-                MSDA_CU(cudaStreamWaitEvent(in_b, p->out2[s], 0));
-            }
-        }
-        MSDA_CU(cudaMemcpyAsync(base + lay.value, (const char *)h_value + n0 * vb, nb * vb, cudaMemcpyHostToDevice, in_a));
-        MSDA_CU(cudaMemcpyAsync(base + lay.loc, (const char *)h_loc + n0 * lb, nb * lb, cudaMemcpyHostToDevice, in_b));
-        MSDA_CU(cudaMemcpyAsync(base + lay.attn, (const char *)h_attn + n0 * ab, nb * ab, cudaMemcpyHostToDevice, in_a));
-        MSDA_CU(cudaMemcpyAsync(base + lay.grad_out, (const char *)h_grad_out + n0 * ob, nb * ob, cudaMemcpyHostToDevice, in_b));
-        MSDA_CU(cudaEventRecord(p->in[s], in_a));
-        MSDA_CU(cudaStreamWaitEvent(st, p->in[s], 0));
-        if (dual) {
-            MSDA_CU(cudaEventRecord(p->in2[s], in_b));
-            MSDA_CU(cudaStreamWaitEvent(st, p->in2[s], 0));
-        }
+        if (chunk >= kHostStages) MSDA_CU(cudaStreamWaitEvent(p.s_in, p.out[s], 0));          // stage drained
+        MSDA_CU(cudaMemcpyAsync(base + lay.value, (const char *)h_value + n0 * vb, nb * vb, cudaMemcpyHostToDevice, p.s_in));
+        MSDA_CU(cudaMemcpyAsync(base + lay.loc, (const char *)h_loc + n0 * lb, nb * lb, cudaMemcpyHostToDevice, p.s_in));
+        MSDA_CU(cudaMemcpyAsync(base + lay.attn, (const char *)h_attn + n0 * ab, nb * ab, cudaMemcpyHostToDevice, p.s_in));
+        MSDA_CU(cudaMemcpyAsync(base + lay.grad_out, (const char *)h_grad_out + n0 * ob, nb * ob, cudaMemcpyHostToDevice, p.s_in));
+        MSDA_CU(cudaEventRecord(p.in[s], p.s_in));
+        MSDA_CU(cudaStreamWaitEvent(st, p.in[s], 0));
         Dims dc = c.d;
         dc.N = nb;
         int rc = c.empty_out ? 0 : launch_forward(dt, base + lay.value, shapes, lsi, base + lay.loc, base + lay.attn,
                                                   base + lay.out, dc, true, st);
         if (rc) return cuda_result(rc, fn);
         rc = launch_backward(dt, base + lay.value, shapes, lsi, base + lay.loc, base + lay.attn, base + lay.grad_out,
-                             base + lay.gv, base + lay.gl, base + lay.ga, dc, true, st);
+                             base + lay.gv, base + lay.gl, base + lay.ga, base + lay.scratch, dc, true, st);
         if (rc) return cuda_result(rc, fn);
-        MSDA_CU(cudaEventRecord(p->cmp[s], st));
-        MSDA_CU(cudaStreamWaitEvent(out_a, p->cmp[s], 0));
-        if (dual) MSDA_CU(cudaStreamWaitEvent(out_b, p->cmp[s], 0));
-        MSDA_CU(cudaMemcpyAsync((char *)h_out + n0 * ob, base + lay.out, nb * ob, cudaMemcpyDeviceToHost, out_a));
-        MSDA_CU(cudaMemcpyAsync((char *)h_gv + n0 * gvb, base + lay.gv, nb * gvb, cudaMemcpyDeviceToHost, out_b));
-        MSDA_CU(cudaMemcpyAsync((char *)h_gl + n0 * lb, base + lay.gl, nb * lb, cudaMemcpyDeviceToHost, out_a));
-        MSDA_CU(cudaMemcpyAsync((char *)h_ga + n0 * ab, base + lay.ga, nb * ab, cudaMemcpyDeviceToHost, out_b));
-        MSDA_CU(cudaEventRecord(p->out[s], out_a));
-        if (dual) MSDA_CU(cudaEventRecord(p->out2[s], out_b));
+        MSDA_CU(cudaEventRecord(p.cmp[s], st));
+        MSDA_CU(cudaStreamWaitEvent(p.s_out, p.cmp[s], 0));
+        MSDA_CU(cudaMemcpyAsync((char *)h_out + n0 * ob, base + lay.out, nb * ob, cudaMemcpyDeviceToHost, p.s_out));
+        MSDA_CU(cudaMemcpyAsync((char *)h_gv + n0 * vb, base + lay.gv, nb * vb, cudaMemcpyDeviceToHost, p.s_out));
+        MSDA_CU(cudaMemcpyAsync((char *)h_gl + n0 * lb, base + lay.gl, nb * lb, cudaMemcpyDeviceToHost, p.s_out));
+        MSDA_CU(cudaMemcpyAsync((char *)h_ga + n0 * ab, base + lay.ga, nb * ab, cudaMemcpyDeviceToHost, p.s_out));
+        MSDA_CU(cudaEventRecord(p.out[s], p.s_out));
     }
-    MSDA_CU(cudaEventRecord(p->done, out_a));
-    MSDA_CU(cudaStreamWaitEvent(st, p->done, 0));
-    if (dual) {
-        MSDA_CU(cudaEventRecord(p->done2, out_b));
-        MSDA_CU(cudaStreamWaitEvent(st, p->done2, 0));
-    }
+    MSDA_CU(cudaEventRecord(p.done, p.s_out));
+    p.has_prev = true;
+    MSDA_CU(cudaStreamWaitEvent(st, p.done, 0));
     return cuda_result(0, fn);
 }
 
@@ -310,48 +317,67 @@ using namespace msda;
     const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,              \
         const void *sampling_loc, const void *attn_weight, const void *grad_out, void *grad_value,   \
         void *grad_loc, void *grad_attn, int N, int S, int M, int D, int L, int Lq, int P, void *stream
-#define BWD_PASS                                                                                     \
-    value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_out, grad_value,       \
-        grad_loc, grad_attn, N, S, M, D, L, Lq, P, stream
+#define BWD_PTRS value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_out, grad_value, grad_loc, grad_attn
 
 extern "C" {
 
 int msda_forward_f32(FWD_ARGS) { return forward_impl("msda_forward_f32", DType::F32, FWD_PASS); }
 int msda_forward_f64(FWD_ARGS) { return forward_impl("msda_forward_f64", DType::F64, FWD_PASS); }
 int msda_forward_bf16(FWD_ARGS) { return forward_impl("msda_forward_bf16", DType::BF16, FWD_PASS); }
-int msda_backward_f32(BWD_ARGS) { return backward_impl("msda_backward_f32", DType::F32, BWD_PASS); }
-int msda_backward_f64(BWD_ARGS) { return backward_impl("msda_backward_f64", DType::F64, BWD_PASS); }
-int msda_backward_bf16(BWD_ARGS) { return backward_impl("msda_backward_bf16", DType::BF16, BWD_PASS); }
+int msda_backward_f32(BWD_ARGS)
+{
+    return backward_impl("msda_backward_f32", DType::F32, BWD_PTRS, nullptr, N, S, M, D, L, Lq, P, stream);
+}
+int msda_backward_f64(BWD_ARGS)
+{
+    return backward_impl("msda_backward_f64", DType::F64, BWD_PTRS, nullptr, N, S, M, D, L, Lq, P, stream);
+}
+int msda_backward_bf16(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *sampling_loc, const void *attn_weight, const void *grad_out, void *grad_value,
+                       void *grad_loc, void *grad_attn, void *scratch_f32, int N, int S, int M, int D, int L, int Lq,
+                       int P, void *stream)
+{
+    return backward_impl("msda_backward_bf16", DType::BF16, BWD_PTRS, scratch_f32, N, S, M, D, L, Lq, P, stream);
+}
+
+size_t msda_backward_bf16_scratch_bytes(int N, int S, int M, int D, int L, int Lq, int P, int pointers_aligned16)
+{
+    if (N < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0) return 0;
+    const Dims d{N, S, M, D, L, Lq, P};
+    return backward_needs_scratch(d, DType::BF16, pointers_aligned16 != 0) ? (size_t)N * S * M * D * 4 : 0;
+}
 
 #define FUSED_FWD_ARGS                                                                               \
     const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,              \
-        const void *reference_points, const void *sampling_offsets, const void *attn_logits, void *out, \
+        const void *reference_points, int ref_dim, const void *sampling_offsets, const void *attn_logits, void *out, \
         int N, int S, int M, int D, int L, int Lq, int P, void *stream
-#define FUSED_BWD_ARGS                                                                               \
+#define FUSED_BWD_PTRS                                                                               \
     const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,              \
-        const void *reference_points, const void *sampling_offsets, const void *attn_logits,         \
-        const void *grad_out, void *grad_value, void *grad_offsets, void *grad_logits, int N, int S, \
-        int M, int D, int L, int Lq, int P, void *stream
+        const void *reference_points, int ref_dim, const void *sampling_offsets, const void *attn_logits, \
+        const void *grad_out, void *grad_value, void *grad_offsets, void *grad_logits
 
 int msda_forward_fused_f32(FUSED_FWD_ARGS)
 {
     return fused_impl("msda_forward_fused_f32", DType::F32, false, value, spatial_shapes, level_start_index, reference_points,
-                      sampling_offsets, attn_logits, nullptr, out, nullptr, nullptr, N, S, M, D, L, Lq, P, stream);
+                      ref_dim, sampling_offsets, attn_logits, nullptr, out, nullptr, nullptr, nullptr, N, S, M, D, L, Lq, P, stream);
 }
 int msda_forward_fused_bf16(FUSED_FWD_ARGS)
 {
     return fused_impl("msda_forward_fused_bf16", DType::BF16, false, value, spatial_shapes, level_start_index, reference_points,
-                      sampling_offsets, attn_logits, nullptr, out, nullptr, nullptr, N, S, M, D, L, Lq, P, stream);
+                      ref_dim, sampling_offsets, attn_logits, nullptr, out, nullptr, nullptr, nullptr, N, S, M, D, L, Lq, P, stream);
 }
-int msda_backward_fused_f32(FUSED_BWD_ARGS)
+int msda_backward_fused_f32(FUSED_BWD_PTRS, int N, int S, int M, int D, int L, int Lq, int P, void *stream)
 {
     return fused_impl("msda_backward_fused_f32", DType::F32, true, value, spatial_shapes, level_start_index, reference_points,
-                      sampling_offsets, attn_logits, grad_out, grad_value, grad_offsets, grad_logits, N, S, M, D, L, Lq, P, stream);
+                      ref_dim, sampling_offsets, attn_logits, grad_out, grad_value, grad_offsets, grad_logits, nullptr, N, S, M,
+                      D, L, Lq, P, stream);
 }
-int msda_backward_fused_bf16(FUSED_BWD_ARGS)
+int msda_backward_fused_bf16(FUSED_BWD_PTRS, void *scratch_f32, int N, int S, int M, int D, int L, int Lq, int P,
+                             void *stream)
 {
     return fused_impl("msda_backward_fused_bf16", DType::BF16, true, value, spatial_shapes, level_start_index, reference_points,
-                      sampling_offsets, attn_logits, grad_out, grad_value, grad_offsets, grad_logits, N, S, M, D, L, Lq, P, stream);
+                      ref_dim, sampling_offsets, attn_logits, grad_out, grad_value, grad_offsets, grad_logits, scratch_f32, N, S,
+                      M, D, L, Lq, P, stream);
 }
 
 #define HOST_ARGS                                                                                              \
@@ -377,7 +403,11 @@ int msda_abi_version(void) { return MSDA_ABI_VERSION; }
 
 const char *msda_build_info(void)
 {
+#ifdef MSDA_AB
+    return "libmsda_b200 sm_100a nvcc " MSDA_STR(__CUDACC_VER_MAJOR__) "." MSDA_STR(__CUDACC_VER_MINOR__) " built " __DATE__ " +AB flavours";
+#else
     return "libmsda_b200 sm_100a nvcc " MSDA_STR(__CUDACC_VER_MAJOR__) "." MSDA_STR(__CUDACC_VER_MINOR__) " built " __DATE__;
+#endif
 }
 
 const char *msda_last_error(void) { return t_err; }
@@ -391,7 +421,6 @@ static int *tuning_slot(const char *key)
     if (!strcmp(key, "bwd_variant")) return &tuning().bwd_variant;
     if (!strcmp(key, "fwd_pipe")) return &tuning().fwd_pipe;
     if (!strcmp(key, "bwd_pipe")) return &tuning().bwd_pipe;
-    if (!strcmp(key, "host_pipe")) return &tuning().host_pipe;
     return nullptr;
 }
 
@@ -411,22 +440,14 @@ int msda_get_tuning(const char *key)
 
 static DType dtype_of(int bits, int is_bf16) { return is_bf16 ? DType::BF16 : (bits == 64 ? DType::F64 : DType::F32); }
 
-const char *msda_describe_forward(int dtype_bits, int is_bf16, int D, int L, int P)
+const char *msda_describe_forward(int dtype_bits, int is_bf16, int N, int M, int D, int L, int P, int Lq)
 {
-    return forward_kernel_name(dtype_of(dtype_bits, is_bf16), D, L, P, true);
+    return forward_kernel_name(dtype_of(dtype_bits, is_bf16), Dims{N, 1, M, D, L, Lq, P}, true);
 }
 
-const char *msda_describe_backward(int dtype_bits, int is_bf16, int D, int L, int P)
+const char *msda_describe_backward(int dtype_bits, int is_bf16, int N, int M, int D, int L, int P, int Lq)
 {
-    return backward_kernel_name(dtype_of(dtype_bits, is_bf16), D, L, P, true);
-}
-
-const char *msda_describe_backward_lq(int dtype_bits, int is_bf16, int D, int L, int P, int Lq)
-{
-    const DType dt = dtype_of(dtype_bits, is_bf16);
-    const Dims d{1, 1, 1, D, L, Lq, P};
-    if (binned_backward_applies(d, dt, true)) return dt == DType::BF16 ? "bwd_bin_bf16" : "bwd_bin_f32";
-    return backward_kernel_name(dt, D, L, P, true);
+    return backward_kernel_name(dtype_of(dtype_bits, is_bf16), Dims{N, 1, M, D, L, Lq, P}, true);
 }
 
 }  // extern "C"

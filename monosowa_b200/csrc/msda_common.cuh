@@ -91,6 +91,18 @@ __device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float 
                  : "memory");
 }
 
+// REDG.E.ADD.BF16x4: the same reduction into a bf16 gradient (short query sets with bf16 values, msda_backward.cu)
+__device__ __forceinline__ void red_add_bf16x4(__nv_bfloat16 *p, float a, float b, float c, float d)
+{
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    asm volatile("red.global.add.noftz.v2.bf16x2 [%0], {%1, %2};" ::"l"(p), "r"(*reinterpret_cast<const unsigned *>(&lo)),
+                 "r"(*reinterpret_cast<const unsigned *>(&hi))
+                 : "memory");
+}
+
+__device__ __forceinline__ void red_add_x4(float *p, float a, float b, float c, float d) { red_add_f32x4(p, a, b, c, d); }
+__device__ __forceinline__ void red_add_x4(__nv_bfloat16 *p, float a, float b, float c, float d) { red_add_bf16x4(p, a, b, c, d); }
+
 // ---- lane-group reduce-scatter ---------------------------------------------------------------
 // G lanes (a power of two, aligned inside the warp) each hold NV partial sums (NV a power of
 // two).  Butterfly: at every step a lane keeps one half of its values and ships the other half
@@ -176,12 +188,12 @@ inline long grid_for(const Dims &d, int order, int qpw, int threads)
 }
 
 // ---- host-side launch plumbing (msda_capi.cu) ------------------------------------------------
+// A/B knobs for measurements (msda_set_tuning); -1 = the shipped default everywhere.
 struct Tuning {
-    int fwd_variant = -1;
-    int bwd_variant = -1;
-    int fwd_pipe = -1;
+    int fwd_variant = -1;   // 11 record kernel always, 12 tile kernel always, 99 generic
+    int bwd_variant = -1;   // 11 record kernel always, 20 tile kernel always, 21 binned kernel always, 99 generic
+    int fwd_pipe = -1;      // launch flavours, -DMSDA_AB builds only
     int bwd_pipe = -1;
-    int host_pipe = -1;     // host-buffer step: copy streams per direction (1 or 2)
 };
 Tuning &tuning();
 void count_launch(int n = 1);
@@ -189,30 +201,38 @@ void count_launch(int n = 1);
 // dtype tags for the launchers
 enum class DType { F32, F64, BF16 };
 
-// implemented in msda_forward.cu / msda_backward.cu; return cudaError_t
+constexpr int kUnsupported = -1000;     // no kernel of the requested family fits: the caller falls back
+constexpr int kNeedsScratch = -1001;    // bf16 backward: this shape needs the fp32 accumulation buffer
+
+// implemented in msda_forward.cu / msda_backward.cu; return cudaError_t (or one of the two codes above)
 int launch_forward(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi,
                    const void *loc, const void *attn, void *out, const Dims &d, bool vec_ok,
                    cudaStream_t st);
+// grad_value: float for fp32 values, double for fp64, bf16 for bf16 values (`scratch`: fp32 accumulation
+// buffer of N*S*M*D floats when backward_needs_scratch(), else unused)
 int launch_backward(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi,
                     const void *loc, const void *attn, const void *grad_out, void *grad_value,
-                    void *grad_loc, void *grad_attn, const Dims &d, bool vec_ok, cudaStream_t st);
-// fused pre-processing entry points; return kUnsupported when no fused kernel fits
-constexpr int kUnsupported = -1000;
+                    void *grad_loc, void *grad_attn, void *scratch, const Dims &d, bool vec_ok, cudaStream_t st);
+bool backward_needs_scratch(const Dims &d, DType dt, bool vec_ok);
+// fused pre-processing entry points; ref_dim = 2 or 6; kUnsupported when no fused kernel fits
 int launch_forward_fused(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref,
-                         const void *offsets, const void *logits, void *out, const Dims &d, cudaStream_t st);
+                         int ref_dim, const void *offsets, const void *logits, void *out, const Dims &d, cudaStream_t st);
 int launch_backward_fused(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref,
-                          const void *offsets, const void *logits, const void *grad_out, void *grad_value,
-                          void *grad_offsets, void *grad_logits, const Dims &d, cudaStream_t st);
-// msda_backward_binned.cu: coarse levels combined in shared memory (long query sets); grad_value pre-zeroed
+                          int ref_dim, const void *offsets, const void *logits, const void *grad_out, void *grad_value,
+                          void *grad_offsets, void *grad_logits, void *scratch, const Dims &d, cudaStream_t st);
+// msda_backward_tiled.cu: persistent grid over 2-D image tiles, grad_value combined in shared memory (long query
+// sets); grad_value (fp32) pre-zeroed
+// msda_backward_binned.cu: chunks of consecutive queries, the COARSE levels' grad_value combined in shared memory
+// (long query sets: the default); grad_value (fp32) pre-zeroed
 bool binned_backward_applies(const Dims &d, DType dt, bool vec_ok);
 int launch_backward_binned(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
                            const void *attn, const void *grad_out, void *grad_value, void *grad_loc, void *grad_attn,
-                           const Dims &d, const void *ref, cudaStream_t st);
-// msda_forward_resident.cu: coarse levels resident in shared memory (long query sets)
-bool resident_forward_applies(const Dims &d, DType dt, bool vec_ok);
-int launch_forward_resident(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
-                            const void *attn, void *out, const Dims &d, const void *ref, cudaStream_t st);
-const char *forward_kernel_name(DType dt, int D, int L, int P, bool vec_ok);
-const char *backward_kernel_name(DType dt, int D, int L, int P, bool vec_ok);
+                           const Dims &d, const void *ref, int ref_dim, cudaStream_t st);
+bool tiled_backward_applies(const Dims &d, DType dt, bool vec_ok);
+int launch_backward_tiled(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                          const void *attn, const void *grad_out, void *grad_value, void *grad_loc, void *grad_attn,
+                          const Dims &d, const void *ref, int ref_dim, cudaStream_t st);
+const char *forward_kernel_name(DType dt, const Dims &d, bool vec_ok);
+const char *backward_kernel_name(DType dt, const Dims &d, bool vec_ok);
 
 }  // namespace msda

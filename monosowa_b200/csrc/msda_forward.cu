@@ -5,30 +5,100 @@
 // launcher (:923-954).  Same arithmetic per sample (see msda_common.cuh), different machine
 // mapping:
 //   * one lane owns 4 channels (one LDG.E.128 per corner in fp32, LDG.E.64 in bf16) and D/4 lanes
-//     (a "lane group") cover one (query, head); a warp owns 32/G consecutive queries of one head:
-//     neighbouring queries gather neighbouring pixels, so their corner lines coincide in L1;
+//     (a "lane group") cover one (query, head); a warp owns 32/G queries of one head that are
+//     neighbours in the image, so their corner lines coincide in L1;
 //   * the bilinear geometry of a sample is computed ONCE, by one lane of the group, and shared
 //     through a 32-byte shared-memory record (msda_records.cuh) -- the first-generation kernel
 //     recomputed it in all 8 lanes and was instruction-issue bound (profiles/r01_v1_*);
-//   * samples outside the sampling window are compacted away before the gather loop.
-// The op is a gather: no tensor cores; the bound is L1 data-pipe wavefronts.
+//   * samples outside the sampling window are compacted away before the gather loop (they cost
+//     neither loads nor FMAs, and -- like the reference's branch, cuh:288 -- never touch `value`);
+//   * long query sets run a persistent grid over 2-D image tiles (msda_tiles.cuh): fwd_tile_kernel.
+// The op is a gather: no tensor cores; the bound is 128-byte rows through the L1 data pipe.
 #include "msda_common.cuh"
 #include "msda_records.cuh"
+#include "msda_tiles.cuh"
 
 namespace msda {
 
 // ------------------------------------------------------------------------------------------------
-// record kernel (see msda_records.cuh): geometry computed once per sample by
-// one lane, shared through shared memory; any L and P; D in {16, 32, 64}; fp32 or bf16 values.
-// ------------------------------------------------------------------------------------------------
+// One (query, head) per lane group: the body shared by the record kernel (one pass per CTA) and the
+// tile kernel (persistent CTAs).  `grp` = the lane group's record area in shared memory.
 // FUSED: `loc` holds the raw sampling offsets, `attn` the raw attention logits and
-// `ref` the (N,Lq,L,2) reference points; locations and softmax weights are formed in registers.
-template <typename VT, int D, int MINB, bool COMPACT, bool FUSED = false, int LOADH = 0>
+// `ref` the (N,Lq,L,ref_dim) reference points; locations and softmax weights are formed in registers.
+// ------------------------------------------------------------------------------------------------
+template <typename VT, int D, bool FUSED, int LOADH>
+__device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const float *__restrict__ loc,
+                                          const float *__restrict__ attn, VT *__restrict__ out,
+                                          const float *__restrict__ ref, const int ref_dim, const Dims &d,
+                                          const LevelInfo *s_lv, uint32_t *grp, const bool valid, const int n,
+                                          const int q, const int m, const int gl, const int k)
+{
+    constexpr int G = D / kChannelsPerLane;
+    using RL = RecordLayout<G>;
+    const int LP = d.L * d.P;
+    const long qm = ((long)n * d.Lq + q) * d.M + m;
+    const VT *vimg = value + ((long)n * d.S * d.M + m) * D + gl * kChannelsPerLane;
+    const int xs = d.M * D;
+
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (d.S > 0) {
+        float aw[kMaxBatches];                      // FUSED: softmax weights of this lane's samples
+        if constexpr (FUSED) group_softmax<G>(attn, qm * LP, LP, gl, valid, aw);
+        auto fetch = [&](int sidx) -> SampleIn {
+            const bool has = valid && sidx < LP;
+            if constexpr (FUSED) {
+                const int l = has ? sidx / d.P : 0;
+                const SampleIn r = fetch_sample_fused(has, loc, ref, ref_dim, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv,
+                                                      l, d.P, aw[0]);
+                aw[0] = aw[1]; aw[1] = aw[2]; aw[2] = aw[3];          // aw[0] = weight of the next batch
+                return r;
+            } else {
+                return fetch_sample(has, loc, attn, qm * LP + sidx);
+            }
+        };
+        SampleIn in = fetch(gl);
+        for (int b0 = 0; b0 < LP; b0 += G) {
+            const int sidx = b0 + gl;
+            // live records only, packed to the front of the group's area
+            __align__(16) uint32_t tmp[8];
+            const SampleGeom gm = build_record(tmp, tmp + 4, valid && sidx < LP, in, s_lv, sidx / d.P, xs);
+            const unsigned gmask = (__ballot_sync(kFullMask, gm.live) >> (k * G)) & ((G == 32) ? ~0u : ((1u << G) - 1u));
+            const int slot = __popc(gmask & ((1u << gl) - 1u));
+            const int cnt = __popc(gmask);
+            if (gm.live) {
+                *reinterpret_cast<int4 *>(grp + slot * 4) = *reinterpret_cast<const int4 *>(tmp);
+                *reinterpret_cast<float4 *>(grp + RL::WEIGHTS + slot * 4) = *reinterpret_cast<const float4 *>(tmp + 4);
+            }
+            __syncwarp();
+            in = fetch(sidx + G);                                     // next batch, in flight
+            for (int s = 0; s < cnt; ++s) {
+                const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
+                const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
+                float v00[4], v01[4], v10[4], v11[4];
+                Vec4<VT>::template gather<LOADH>(vimg + off.x, v00);
+                Vec4<VT>::template gather<LOADH>(vimg + off.y, v01);
+                Vec4<VT>::template gather<LOADH>(vimg + off.z, v10);
+                Vec4<VT>::template gather<LOADH>(vimg + off.w, v11);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
+            }
+            __syncwarp();
+        }
+    }
+    if (valid) Vec4<VT>::store(out + qm * D + gl * kChannelsPerLane, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// record kernel: one pass, a CTA's 8 warps cover 8 * 32/G consecutive queries of one head.
+// Any L and P; D in {16, 32, 64}; fp32 or bf16 values.  Used for short query sets (the decoder).
+// ------------------------------------------------------------------------------------------------
+template <typename VT, int D, int MINB, bool FUSED = false, int LOADH = 0>
 __global__ void __launch_bounds__(256, MINB)
 fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                const float *__restrict__ attn, VT *__restrict__ out, const Dims d, const int order,
-               const float *__restrict__ ref = nullptr)
+               const float *__restrict__ ref = nullptr, const int ref_dim = 2)
 {
     constexpr int G = D / kChannelsPerLane;
     using RL = RecordLayout<G>;
@@ -44,81 +114,54 @@ fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     WorkItem w = decode_work<QPW>(d, order, k);
     if (__ballot_sync(kFullMask, w.valid) == 0) return;
     if (!w.valid) { w.n = 0; w.q = 0; w.m = 0; }
-
-    const int LP = d.L * d.P;
-    const long qm = ((long)w.n * d.Lq + w.q) * d.M + w.m;
-    const VT *vimg = value + ((long)w.n * d.S * d.M + w.m) * D + gl * kChannelsPerLane;
-    const int xs = d.M * D;
     uint32_t *grp = s_rec + (threadIdx.x >> 5) * RL::WARP_WORDS + k * RL::GROUP_WORDS;
+    fwd_group<VT, D, FUSED, LOADH>(value, loc, attn, out, ref, ref_dim, d, s_lv, grp, w.valid, w.n, w.q, w.m, gl, k);
+}
 
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (d.S > 0) {
-        float aw[kMaxBatches];                      // FUSED: softmax weights of this lane's samples
-        if constexpr (FUSED) group_softmax<G>(attn, qm * LP, LP, gl, w.valid, aw);
-        auto fetch = [&](int sidx) -> SampleIn {
-            const bool has = w.valid && sidx < LP;
-            if constexpr (FUSED) {
-                const int l = has ? sidx / d.P : 0;
-                const SampleIn r = fetch_sample_fused(has, loc, ref, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l, aw[0]);
-                aw[0] = aw[1]; aw[1] = aw[2]; aw[2] = aw[3];          // aw[0] = weight of the next batch
-                return r;
-            } else {
-                return fetch_sample(has, loc, attn, qm * LP + sidx);
-            }
-        };
-        SampleIn in = fetch(gl);
-        for (int b0 = 0; b0 < LP; b0 += G) {
-            const int sidx = b0 + gl;
-            if constexpr (COMPACT) {
-                // live records only, packed to the front of the group's area: samples outside the
-                // window cost neither loads nor FMAs (15 % of them at MonoDETR's shapes)
-                __align__(16) uint32_t tmp[8];
-                const SampleGeom gm = build_record(tmp, tmp + 4, w.valid && sidx < LP, in, s_lv, sidx / d.P, xs);
-                const unsigned gmask = (__ballot_sync(kFullMask, gm.live) >> (k * G)) & ((G == 32) ? ~0u : ((1u << G) - 1u));
-                const int slot = __popc(gmask & ((1u << gl) - 1u));
-                const int cnt = __popc(gmask);
-                if (gm.live) {
-                    *reinterpret_cast<int4 *>(grp + slot * 4) = *reinterpret_cast<const int4 *>(tmp);
-                    *reinterpret_cast<float4 *>(grp + RL::WEIGHTS + slot * 4) = *reinterpret_cast<const float4 *>(tmp + 4);
-                }
-                __syncwarp();
-                in = fetch(sidx + G);
-                for (int s = 0; s < cnt; ++s) {
-                    const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
-                    const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
-                    float v00[4], v01[4], v10[4], v11[4];
-                    Vec4<VT>::template gather<LOADH>(vimg + off.x, v00);
-                    Vec4<VT>::template gather<LOADH>(vimg + off.y, v01);
-                    Vec4<VT>::template gather<LOADH>(vimg + off.z, v10);
-                    Vec4<VT>::template gather<LOADH>(vimg + off.w, v11);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
-                }
-                __syncwarp();
-                continue;
-            }
-            build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, w.valid && sidx < LP, in, s_lv, sidx / d.P, xs);
-            __syncwarp();
-            in = fetch(sidx + G);                                     // next batch, in flight
-#pragma unroll
-            for (int s = 0; s < G; ++s) {
-                const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
-                const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
-                float v00[4], v01[4], v10[4], v11[4];
-                Vec4<VT>::template gather<LOADH>(vimg + off.x, v00);
-                Vec4<VT>::template gather<LOADH>(vimg + off.y, v01);
-                Vec4<VT>::template gather<LOADH>(vimg + off.z, v10);
-                Vec4<VT>::template gather<LOADH>(vimg + off.w, v11);
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
-            }
-            __syncwarp();
+#ifdef MSDA_AB
+// ------------------------------------------------------------------------------------------------
+// tile kernel (measurement build only, see use_tile below): persistent CTAs walk (image, head, 2-D image tile) work items (msda_tiles.cuh); all warps
+// of a CTA work on the same tile, pass after pass, so the rows they gather are each other's L1 hits.
+// ------------------------------------------------------------------------------------------------
+template <typename VT, int D, int THREADS, int MINB, bool FUSED = false, int LOADH = 0>
+__global__ void __launch_bounds__(THREADS, MINB)
+fwd_tile_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
+                const int64_t *__restrict__ lsi, const float *__restrict__ loc,
+                const float *__restrict__ attn, VT *__restrict__ out, const Dims d,
+                const float *__restrict__ ref, const int ref_dim)
+{
+    constexpr int G = D / kChannelsPerLane;
+    using RL = RecordLayout<G>;
+    constexpr int QPW = RL::QPW, WARPS = THREADS / 32;
+    static_assert(G >= 2 && G <= 32 && (32 % G) == 0, "unsupported D");
+
+    __shared__ LevelInfo s_lv[MSDA_MAX_LEVELS];
+    __shared__ TilePlan s_plan;
+    __shared__ TileItem s_item;
+    __shared__ __align__(16) uint32_t s_rec[WARPS * RL::WARP_WORDS];
+    stage_levels(s_lv, shapes, lsi, d.L);
+    if (threadIdx.x == 0) make_tile_plan(s_plan, s_lv, d, 256);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane % G, k = lane / G;
+    uint32_t *grp = s_rec + warp * RL::WARP_WORDS + k * RL::GROUP_WORDS;
+    const long n_items = (long)d.N * d.M * s_plan.n_tiles;
+
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        __syncthreads();                                        // everyone is done with the previous item
+        if (threadIdx.x == 0) make_tile_item(s_item, s_plan, s_lv, d, item);
+        __syncthreads();
+        const int nq = s_item.nq, n = s_item.n, m = s_item.m;
+        for (int i0 = warp * QPW; i0 < nq; i0 += WARPS * QPW) {
+            const bool valid = i0 + k < nq;
+            const int q = valid ? tile_query(s_item, s_plan, s_lv, d.L, i0 + k) : 0;
+            fwd_group<VT, D, FUSED, LOADH>(value, loc, attn, out, ref, ref_dim, d, s_lv, grp, valid, n, q, m, gl, k);
         }
     }
-    if (w.valid) Vec4<VT>::store(out + qm * D + gl * kChannelsPerLane, acc);
 }
+
+#endif  // MSDA_AB
 
 // ------------------------------------------------------------------------------------------------
 // generic kernel: any D / P / alignment; VT value type, CT coordinate + arithmetic type.
@@ -186,63 +229,94 @@ fwd_generic_kernel(const VT *__restrict__ value, const int64_t *__restrict__ sha
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-template <typename VT, int D>
-int run_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
-            const float *attn, VT *out, const Dims &d, int order, cudaStream_t st)
+// fwd_variant: -1 / 11 record kernel; 12 tile kernel (opt-in, see use_tile); 99 generic.  fwd_pipe selects A/B launch flavours in -DMSDA_AB builds only.
+inline bool rec_supported(const Dims &d) { return d.D == 16 || d.D == 32 || d.D == 64; }
+
+bool use_rec(const Dims &d, bool vec_ok)
+{
+    return vec_ok && tuning().fwd_variant != 99 && rec_supported(d) && (long)d.S * d.M * d.D < (1L << 31);
+}
+
+// Measured on B200 at configs[1] (profiles/r02_sweep_tile_vs_rec.jsonl, r02_ncu_tile_v1_summary.md): the tile kernel
+// raises the L1 hit rate from 0 to 70 % and cuts L2->SM traffic 3.5x, yet runs 0.64 ms against the record kernel's
+// 0.53 ms -- both execute the same ~0.42 ms worth of L1 data-pipe wavefronts (a row costs a wavefront whether it
+// hits L1 or arrives from L2) and the persistent loop hides latency worse.  The forward is bound by the number of
+// rows through the pipe, not by where they come from; the record kernel stays the default for every Lq and the
+// tile kernel exists only in the measurement build (-DMSDA_AB, fwd_variant = 12), where tests keep it covered.
+bool use_tile(const Dims &d)
+{
+    (void)d;
+#ifdef MSDA_AB
+    return tuning().fwd_variant == 12;
+#else
+    return false;
+#endif
+}
+
+template <typename VT, int D, bool FUSED>
+int run_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn, VT *out,
+            const Dims &d, const float *ref, int ref_dim, cudaStream_t st)
 {
     constexpr int QPW = 32 / (D / kChannelsPerLane);
-    const int threads = 256;                       // s_rec is sized for 8 warps
-    const long grid = grid_for(d, order, QPW, threads);
-    // fwd_pipe = requested minimum CTAs/SM (register cap 64K / (256 * MINB)); trades ILP for TLP
-#define MSDA_FWD_REC(MINB, COMPACT) \
-    fwd_rec_kernel<VT, D, MINB, COMPACT><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order)
-    // Default, measured on B200 at configs[1] (profiles/r01_v2_compact_sweep.jsonl, r01_loadhint_sweep.jsonl):
-    // fp32 -- compacting loop at <= 48 registers (5 CTAs/SM) with L1::no_allocate gathers 0.529 ms (0.592 with
-    // allocating loads: L1 fills compete with the gather for the data pipe, hits are still served);
-    // bf16 -- unrolled loop at <= 40 registers with allocating loads 0.493 ms (hints make no difference there).
-    int flavour = tuning().fwd_pipe;
-    if (flavour < 0) flavour = sizeof(VT) == 4 ? 25 : 6;
-    switch (flavour) {
-    case 3: MSDA_FWD_REC(3, false); break;
-    case 5: MSDA_FWD_REC(5, false); break;
-    case 6: MSDA_FWD_REC(6, false); break;
-    case 15: MSDA_FWD_REC(5, true); break;
-#define MSDA_FWD_REC_H(MINB, COMPACT, H) \
-    fwd_rec_kernel<VT, D, MINB, COMPACT, false, H><<<(unsigned)grid, threads, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order)
-    case 25: MSDA_FWD_REC_H(5, true, 1); break;
-    case 35: MSDA_FWD_REC_H(5, true, 2); break;
-    case 26: MSDA_FWD_REC_H(6, false, 1); break;
-    case 36: MSDA_FWD_REC_H(6, false, 2); break;
-    case 24: MSDA_FWD_REC_H(4, true, 1); break;
-    case 27: MSDA_FWD_REC_H(6, true, 1); break;
-#undef MSDA_FWD_REC_H
-    case 14: MSDA_FWD_REC(4, true); break;
-    case 16: MSDA_FWD_REC(6, true); break;
-    default: MSDA_FWD_REC(4, false); break;
-    }
-#undef MSDA_FWD_REC
+    const long grid = grid_for(d, 1, QPW, 256);
+    if (grid > 0x7fffffffL) return kUnsupported;
+    // measured on B200 at configs[1] (profiles/r01_v2_compact_sweep.jsonl, r01_loadhint_sweep.jsonl): the compacting
+    // loop at <= 48 registers (5 CTAs/SM); fp32 gathers with L1::no_allocate (a strip of consecutive queries has
+    // little reuse, fills only compete with the gather for the data pipe), bf16 with allocating loads
+    constexpr int LOADH = sizeof(VT) == 4 ? 1 : 0;
+    fwd_rec_kernel<VT, D, 5, FUSED, LOADH><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
     count_launch();
     return (int)cudaGetLastError();
 }
 
-template <typename VT>
-int dispatch_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
-                 const void *attn, void *out, const Dims &d, int order, cudaStream_t st)
+template <typename VT, int D, bool FUSED>
+int run_tile(const VT *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn, VT *out,
+             const Dims &d, const float *ref, int ref_dim, cudaStream_t st)
 {
-    const VT *v = (const VT *)value;
-    const float *lo = (const float *)loc, *at = (const float *)attn;
-    VT *o = (VT *)out;
-    switch (d.D) {
-    case 16: return run_rec<VT, 16>(v, shapes, lsi, lo, at, o, d, order, st);
-    case 32: return run_rec<VT, 32>(v, shapes, lsi, lo, at, o, d, order, st);
-    case 64: return run_rec<VT, 64>(v, shapes, lsi, lo, at, o, d, order, st);
+#ifndef MSDA_AB
+    (void)value; (void)shapes; (void)lsi; (void)loc; (void)attn; (void)out; (void)d; (void)ref; (void)ref_dim; (void)st;
+    return kUnsupported;
+#else
+#define MSDA_FWD_TILE(THREADS, MINB, H)                                                                     \
+    fwd_tile_kernel<VT, D, THREADS, MINB, FUSED, H><<<persistent_grid(MINB), THREADS, 0, st>>>(             \
+        value, shapes, lsi, loc, attn, out, d, ref, ref_dim)
+    switch (tuning().fwd_pipe) {
+    case 1: MSDA_FWD_TILE(256, 5, 1); break;
+    case 2: MSDA_FWD_TILE(512, 2, 0); break;
+    case 3: MSDA_FWD_TILE(512, 2, 1); break;
+    case 4: MSDA_FWD_TILE(1024, 1, 0); break;
+    case 5: MSDA_FWD_TILE(1024, 1, 1); break;
+    case 6: MSDA_FWD_TILE(256, 4, 0); break;
+    case 7: MSDA_FWD_TILE(256, 6, 0); break;
+    case 8: MSDA_FWD_TILE(512, 3, 0); break;
+    default: MSDA_FWD_TILE(256, 5, 0); break;
     }
-    return (int)cudaErrorInvalidValue;
+#undef MSDA_FWD_TILE
+    count_launch();
+    return (int)cudaGetLastError();
+#endif
 }
 
-// fwd_variant: -1 default (record kernel, work order 1); 10/11 record kernel with order 0/1; 99 generic.
-inline bool rec_supported(const Dims &d) { return d.D == 16 || d.D == 32 || d.D == 64; }
-inline bool want_rec(int variant) { return variant != 99; }
+template <typename VT, bool FUSED>
+int dispatch_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
+                 void *out, const Dims &d, const void *ref, int ref_dim, cudaStream_t st)
+{
+    const VT *v = (const VT *)value;
+    const float *lo = (const float *)loc, *at = (const float *)attn, *rf = (const float *)ref;
+    VT *o = (VT *)out;
+    const bool tile = use_tile(d);
+#define MSDA_FWD_D(DD)                                                                            \
+    case DD:                                                                                      \
+        return tile ? run_tile<VT, DD, FUSED>(v, shapes, lsi, lo, at, o, d, rf, ref_dim, st)      \
+                    : run_rec<VT, DD, FUSED>(v, shapes, lsi, lo, at, o, d, rf, ref_dim, st)
+    switch (d.D) {
+        MSDA_FWD_D(16);
+        MSDA_FWD_D(32);
+        MSDA_FWD_D(64);
+    }
+#undef MSDA_FWD_D
+    return kUnsupported;
+}
 
 template <typename VT, typename CT>
 int run_generic(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
@@ -251,71 +325,31 @@ int run_generic(const void *value, const int64_t *shapes, const int64_t *lsi, co
     const long total = (long)d.N * d.Lq * d.M * d.D;
     const int threads = 256;
     const long grid = (total + threads - 1) / threads;
+    if (grid > 0x7fffffffL) return (int)cudaErrorInvalidConfiguration;
     fwd_generic_kernel<VT, CT><<<(unsigned)grid, threads, 0, st>>>(
         (const VT *)value, shapes, lsi, (const CT *)loc, (const CT *)attn, (VT *)out, d);
     count_launch();
     return (int)cudaGetLastError();
 }
 
-bool use_rec(const Dims &d, bool vec_ok)
-{
-    return vec_ok && want_rec(tuning().fwd_variant) && rec_supported(d) && (long)d.S * d.M * d.D < (1L << 31);
-}
-
-}  // namespace
-
-namespace {
-template <typename VT, int D>
-int run_rec_fused(const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref, const void *offsets,
-                  const void *logits, void *out, const Dims &d, cudaStream_t st)
-{
-    constexpr int G = D / kChannelsPerLane;
-    if (d.L * d.P > kMaxBatches * G) return kUnsupported;
-    const long grid = grid_for(d, 1, 32 / G, 256);
-    if (sizeof(VT) == 4)
-        fwd_rec_kernel<VT, D, 5, true, true, 1><<<(unsigned)grid, 256, 0, st>>>(
-            (const VT *)value, shapes, lsi, (const float *)offsets, (const float *)logits, (VT *)out, d, 1, (const float *)ref);
-    else
-        fwd_rec_kernel<VT, D, 6, false, true><<<(unsigned)grid, 256, 0, st>>>(
-            (const VT *)value, shapes, lsi, (const float *)offsets, (const float *)logits, (VT *)out, d, 1, (const float *)ref);
-    count_launch();
-    return (int)cudaGetLastError();
-}
 }  // namespace
 
 int launch_forward_fused(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref,
-                         const void *offsets, const void *logits, void *out, const Dims &d, cudaStream_t st)
+                         int ref_dim, const void *offsets, const void *logits, void *out, const Dims &d, cudaStream_t st)
 {
-    if ((long)d.S * d.M * d.D >= (1L << 31) || dt == DType::F64) return kUnsupported;
-    if (resident_forward_applies(d, dt, true)) return launch_forward_resident(dt, value, shapes, lsi, offsets, logits, out, d, ref, st);
-#define FUSED_ARGS value, shapes, lsi, ref, offsets, logits, out, d, st
-    if (dt == DType::F32) {
-        switch (d.D) {
-        case 16: return run_rec_fused<float, 16>(FUSED_ARGS);
-        case 32: return run_rec_fused<float, 32>(FUSED_ARGS);
-        case 64: return run_rec_fused<float, 64>(FUSED_ARGS);
-        }
-    } else {
-        switch (d.D) {
-        case 16: return run_rec_fused<__nv_bfloat16, 16>(FUSED_ARGS);
-        case 32: return run_rec_fused<__nv_bfloat16, 32>(FUSED_ARGS);
-        case 64: return run_rec_fused<__nv_bfloat16, 64>(FUSED_ARGS);
-        }
-    }
-#undef FUSED_ARGS
-    return kUnsupported;
+    if ((long)d.S * d.M * d.D >= (1L << 31) || dt == DType::F64 || !rec_supported(d)) return kUnsupported;
+    if (d.L * d.P > kMaxBatches * (d.D / kChannelsPerLane) || (ref_dim != 2 && ref_dim != 6)) return kUnsupported;
+    if (dt == DType::F32) return dispatch_rec<float, true>(value, shapes, lsi, offsets, logits, out, d, ref, ref_dim, st);
+    return dispatch_rec<__nv_bfloat16, true>(value, shapes, lsi, offsets, logits, out, d, ref, ref_dim, st);
 }
 
-const char *forward_kernel_name(DType dt, int D, int L, int P, bool vec_ok)
+const char *forward_kernel_name(DType dt, const Dims &d, bool vec_ok)
 {
-    (void)L;
-    Dims d{1, 1, 1, D, 1, 1, P};
-    switch (dt) {
-    case DType::F64: return "fwd_generic_f64";
-    case DType::F32: return use_rec(d, vec_ok) ? "fwd_rec_f32" : "fwd_generic_f32";
-    case DType::BF16: return use_rec(d, vec_ok) ? "fwd_rec_bf16" : "fwd_generic_bf16";
-    }
-    return "?";
+    if (dt == DType::F64) return "fwd_generic_f64";
+    const bool bf = dt == DType::BF16;
+    if (!use_rec(d, vec_ok)) return bf ? "fwd_generic_bf16" : "fwd_generic_f32";
+    if (use_tile(d)) return bf ? "fwd_tile_bf16" : "fwd_tile_f32";
+    return bf ? "fwd_rec_bf16" : "fwd_rec_f32";
 }
 
 int launch_forward(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi,
@@ -323,11 +357,11 @@ int launch_forward(DType dt, const void *value, const int64_t *shapes, const int
                    cudaStream_t st)
 {
     if (dt == DType::F64) return run_generic<double, double>(value, shapes, lsi, loc, attn, out, d, st);
-    if (resident_forward_applies(d, dt, vec_ok)) return launch_forward_resident(dt, value, shapes, lsi, loc, attn, out, d, nullptr, st);
-    const int rec_order = tuning().fwd_variant == 10 ? 0 : 1;
-    if (dt == DType::F32 && use_rec(d, vec_ok)) return dispatch_rec<float>(value, shapes, lsi, loc, attn, out, d, rec_order, st);
-    if (dt == DType::BF16 && use_rec(d, vec_ok))
-        return dispatch_rec<__nv_bfloat16>(value, shapes, lsi, loc, attn, out, d, rec_order, st);
+    if (use_rec(d, vec_ok)) {
+        const int rc = dt == DType::F32 ? dispatch_rec<float, false>(value, shapes, lsi, loc, attn, out, d, nullptr, 2, st)
+                                        : dispatch_rec<__nv_bfloat16, false>(value, shapes, lsi, loc, attn, out, d, nullptr, 2, st);
+        if (rc != kUnsupported) return rc;                 // grid overflow: the generic kernel takes it
+    }
     if (dt == DType::F32) return run_generic<float, float>(value, shapes, lsi, loc, attn, out, d, st);
     return run_generic<__nv_bfloat16, float>(value, shapes, lsi, loc, attn, out, d, st);
 }

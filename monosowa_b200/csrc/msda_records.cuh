@@ -1,4 +1,4 @@
-// msda_records.cuh -- "shared geometry" building blocks of the second-generation kernels.
+// msda_records.cuh -- "shared geometry" building blocks of the record / tile kernels.
 //
 // Measured on B200 (profiles/r01_v1_ncu_full_summary.md): the first-generation vector kernels
 // were instruction-issue bound -- every one of the G lanes that cover a (query, head) recomputed
@@ -7,15 +7,14 @@
 // 32-byte record into shared memory, and all G lanes then consume the G records of their group
 // with two broadcast LDS.128 per sample:
 //     record = { int32 element offset of the 4 corners (clamped into the map), 4 weights }
-// Consumption is branch-free so that all 4*G corner loads of a batch can be in flight together:
 //   * an invalid corner keeps a clamped (in-map) address and a zero weight -- the clamped pixel is
 //     always one of the sample's own valid corners;
-//   * a sample outside the (-1,H)x(-1,W) window, or past L*P, points at element 0 of the image
-//     (one hot L1 line -- these kernels gather with L1 allocation; measured: pointing such records at
-//     per-query rows, or bypassing L1, is slower) with four zero weights.
-// For finite `value` this is exactly the reference's skip logic (ms_deform_im2col_cuda.cuh:56-80,
-// 288); a NaN/Inf stored at pixel 0 of a head would additionally reach queries that have outside
-// samples (0 * NaN), which the reference's branches avoid -- documented in DESIGN.md.
+//   * the forward packs only the records of samples inside the (-1,H)x(-1,W) window (the reference's
+//     branch, ms_deform_im2col_cuda.cuh:288): outside samples cost nothing and read nothing;
+//   * the backward walks all G records of a batch (it needs a fixed sample -> lane mapping for its
+//     reduce-scatter); an outside sample points at element 0 of the image with four zero weights, its
+//     partial dots are DISCARDED by the owning lane with a select (not multiplied), so a NaN stored
+//     there cannot leak -- the reference's skip logic (cuh:56-80, 288, 365-367) exactly.
 #pragma once
 
 #include "msda_common.cuh"
@@ -124,7 +123,7 @@ struct SampleGeom {
     float a;                    // attention weight
     float Wf, Hf;
     unsigned vmask;             // bit0..3: corner 00, 01, 10, 11 lies inside the map
-    int cell;                   // (y0+1)*(W+1) + (x0+1): the sample's base-corner cell on the (H+1)x(W+1) lattice
+    int cy, cx;                 // (y0+1, x0+1): the sample's base-corner cell on the (H+1)x(W+1) lattice
     bool live;                  // sample exists (index < L*P, query valid) and is inside the window
 };
 
@@ -132,12 +131,13 @@ struct SampleGeom {
 // current batch is consumed).
 struct SampleIn {
     float x, y, a;
+    float ex, ey;               // fused 6-dim reference points only: (l+r, t+b) of the reference box
 };
 
 __device__ __forceinline__ SampleIn fetch_sample(bool has, const float *__restrict__ loc,
                                                  const float *__restrict__ attn, long sample_index)
 {
-    SampleIn in{0.f, 0.f, 0.f};
+    SampleIn in{0.f, 0.f, 0.f, 0.f, 0.f};
     if (has) {
         // read-once streams: keep them from displacing the value lines that the gather re-uses in L1/L2
         const float2 xy = __ldcs(reinterpret_cast<const float2 *>(loc) + sample_index);
@@ -197,39 +197,58 @@ __device__ __forceinline__ void group_softmax(const float *__restrict__ logits, 
     for (int b = 0; b < kMaxBatches; ++b) a[b] = (sum > 0.f) ? a[b] / sum : 0.f;
 }
 
-// fused fetch: offset + reference point -> normalised location (same operation order as torch:
-// ref + off / size, IEEE division); the attention weight comes from group_softmax
+// fused fetch: offset + reference point -> normalised location, same operation order as the reference module
+// (ops/modules/ms_deform_attn.py:149-155), every step rounded (no FMA contraction):
+//   ref_dim 2:  loc = ref + off / (W, H)
+//   ref_dim 6:  loc = ref[:2] + ((off / P) * (ref[2]+ref[3], ref[4]+ref[5])) * 0.5
+// the attention weight comes from group_softmax
 __device__ __forceinline__ SampleIn fetch_sample_fused(bool has, const float *__restrict__ offsets,
-                                                       const float *__restrict__ ref, long sample_index,
-                                                       long ref_index, const LevelInfo *s_lv, int l, float a)
+                                                       const float *__restrict__ ref, int ref_dim, long sample_index,
+                                                       long ref_index, const LevelInfo *s_lv, int l, int P, float a)
 {
-    SampleIn in{0.f, 0.f, 0.f};
+    SampleIn in{0.f, 0.f, 0.f, 0.f, 0.f};
     if (has) {
         const float2 o = __ldcs(reinterpret_cast<const float2 *>(offsets) + sample_index);
-        const float2 r = __ldg(reinterpret_cast<const float2 *>(ref) + ref_index);
-        const LevelInfo li = s_lv[l];
-        in.x = r.x + __fdiv_rn(o.x, (float)li.W);
-        in.y = r.y + __fdiv_rn(o.y, (float)li.H);
+        if (ref_dim == 2) {
+            const float2 r = __ldg(reinterpret_cast<const float2 *>(ref) + ref_index);
+            const LevelInfo li = s_lv[l];
+            in.x = __fadd_rn(r.x, __fdiv_rn(o.x, (float)li.W));
+            in.y = __fadd_rn(r.y, __fdiv_rn(o.y, (float)li.H));
+        } else {
+            const float2 *rp = reinterpret_cast<const float2 *>(ref) + ref_index * 3;
+            const float2 r01 = __ldg(rp), r23 = __ldg(rp + 1), r45 = __ldg(rp + 2);
+            in.ex = __fadd_rn(r23.x, r23.y);
+            in.ey = __fadd_rn(r45.x, r45.y);
+            in.x = __fadd_rn(r01.x, __fmul_rn(__fmul_rn(__fdiv_rn(o.x, (float)P), in.ex), 0.5f));
+            in.y = __fadd_rn(r01.y, __fmul_rn(__fmul_rn(__fdiv_rn(o.y, (float)P), in.ey), 0.5f));
+        }
         in.a = a;
     }
     return in;
 }
 
-// Build the record of one sample and write it to `rec_off` / `rec_w` (16-byte aligned).  The
-// weights stored are w_ij * a (what both forward and grad_value need).  The four offsets are
-// (row0 + y * W + x) * stride | tag: for rows in global memory row0 = the level's start index and
-// stride = M * D; a kernel that keeps a level in shared memory passes the level's first shared row, stride = D
-// and a tag bit that tells the consumer where to read (msda_forward_resident.cu).
-__device__ __forceinline__ SampleGeom build_record_at(uint32_t *rec_off, uint32_t *rec_w, bool has, const SampleIn in,
-                                                      const LevelInfo *s_lv, int l, int row0, int stride, int tag)
+// d loc / d offset applied to a location gradient, in autograd's operation order
+__device__ __forceinline__ float2 fused_offset_grad(int ref_dim, float gx, float gy, float Wf, float Hf, float ex,
+                                                    float ey, int P)
+{
+    if (ref_dim == 2) return make_float2(__fdiv_rn(gx, Wf), __fdiv_rn(gy, Hf));
+    return make_float2(__fdiv_rn(__fmul_rn(__fmul_rn(gx, 0.5f), ex), (float)P),
+                       __fdiv_rn(__fmul_rn(__fmul_rn(gy, 0.5f), ey), (float)P));
+}
+
+// Geometry of one sample: the four corner offsets (lsi_l + y * W + x) * xs, clamped into the map, and the
+// four weights w_ij * a (what both the forward and grad_value need); `off` / `wa` are all zero for a sample
+// that does not exist or lies outside the window.
+__device__ __forceinline__ SampleGeom sample_geometry(bool has, const SampleIn in, const LevelInfo *s_lv, int l, int xs,
+                                                      int4 &off, float4 &wa)
 {
     SampleGeom gm;
     gm.live = false;
     gm.w00 = gm.w01 = gm.w10 = gm.w11 = 0.f;
     gm.hy = gm.ly = gm.hx = gm.lx = 0.f;
-    gm.a = 0.f; gm.Wf = 0.f; gm.Hf = 0.f; gm.vmask = 0u; gm.cell = 0;
-    int4 off = make_int4(0, 0, 0, 0);
-    float4 wa = make_float4(0.f, 0.f, 0.f, 0.f);
+    gm.a = 0.f; gm.Wf = 0.f; gm.Hf = 0.f; gm.vmask = 0u; gm.cy = 0; gm.cx = 0;
+    off = make_int4(0, 0, 0, 0);
+    wa = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has) {
         const float a = in.a;
         const LevelInfo li = s_lv[l];
@@ -247,22 +266,26 @@ __device__ __forceinline__ SampleGeom build_record_at(uint32_t *rec_off, uint32_
             gm.vmask = (y0ok && x0ok ? 1u : 0u) | (y0ok && x1ok ? 2u : 0u) | (y1ok && x0ok ? 4u : 0u) |
                        (y1ok && x1ok ? 8u : 0u);
             gm.live = true;
-            gm.cell = (t.y0 + 1) * (li.W + 1) + t.x0 + 1;
-            const int r0 = (row0 + y0c * li.W) * stride, r1 = (row0 + y1c * li.W) * stride;
-            off = make_int4((r0 + x0c * stride) | tag, (r0 + x1c * stride) | tag, (r1 + x0c * stride) | tag,
-                            (r1 + x1c * stride) | tag);
+            gm.cy = t.y0 + 1;
+            gm.cx = t.x0 + 1;
+            const int r0 = (li.start + y0c * li.W) * xs, r1 = (li.start + y1c * li.W) * xs;
+            off = make_int4(r0 + x0c * xs, r0 + x1c * xs, r1 + x0c * xs, r1 + x1c * xs);
             wa = make_float4(gm.w00 * a, gm.w01 * a, gm.w10 * a, gm.w11 * a);
         }
     }
-    *reinterpret_cast<int4 *>(rec_off) = off;
-    *reinterpret_cast<float4 *>(rec_w) = wa;
     return gm;
 }
 
+// Build the record of one sample and write it to `rec_off` / `rec_w` (16-byte aligned).
 __device__ __forceinline__ SampleGeom build_record(uint32_t *rec_off, uint32_t *rec_w, bool has, const SampleIn in,
                                                    const LevelInfo *s_lv, int l, int xs)
 {
-    return build_record_at(rec_off, rec_w, has, in, s_lv, l, has ? s_lv[l].start : 0, xs, 0);
+    int4 off;
+    float4 wa;
+    const SampleGeom gm = sample_geometry(has, in, s_lv, l, xs, off, wa);
+    *reinterpret_cast<int4 *>(rec_off) = off;
+    *reinterpret_cast<float4 *>(rec_w) = wa;
+    return gm;
 }
 
 }  // namespace msda

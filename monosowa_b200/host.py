@@ -9,7 +9,7 @@ The reference extension has no counterpart (CUDA tensors only, ops/src/ms_deform
 
 ``value`` / ``loc`` / ``attn`` / ``grad_out`` are CPU tensors (pin them for asynchronous copies);
 ``shapes_dev`` / ``lsi_dev`` are int64 CUDA tensors and select the device.  Results are pinned CPU tensors
-(pass ``results=`` to reuse buffers); ``grad_value`` is fp32 also for bf16 values.  No CPU fallback exists.
+(pass ``results=`` to reuse buffers); ``grad_value`` has ``value``'s dtype.  No CPU fallback exists.
 """
 from __future__ import annotations
 
@@ -20,13 +20,13 @@ import torch
 from . import _lib
 
 _SUFFIX = {torch.float32: "f32", torch.bfloat16: "bf16"}
-_workspaces: dict = {}
+_workspaces: dict = {}           # (device, stream) -> staging buffer: concurrent streams never share stages
 
 
-def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
-    ws = _workspaces.get(dev)
+def _workspace(dev: torch.device, stream: int, nbytes: int) -> torch.Tensor:
+    ws = _workspaces.get((dev, stream))
     if ws is None or ws.numel() < nbytes:
-        ws = _workspaces[dev] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = _workspaces[(dev, stream)] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     return ws
 
 
@@ -63,11 +63,11 @@ def host_step(value, spatial_shapes, level_start_index, sampling_locations, atte
         raise RuntimeError("inconsistent shapes")
     if results is None:
         results = (torch.empty((n, lq, m * d), dtype=value.dtype).pin_memory(),
-                   torch.empty(value.shape, dtype=torch.float32).pin_memory(),
+                   torch.empty(value.shape, dtype=value.dtype).pin_memory(),
                    torch.empty(sampling_locations.shape, dtype=torch.float32).pin_memory(),
                    torch.empty(attention_weights.shape, dtype=torch.float32).pin_memory())
     out, gv, gl, ga = results
-    for name, t, numel, dt in (("out", out, n * lq * m * d, value.dtype), ("grad_value", gv, value.numel(), torch.float32),
+    for name, t, numel, dt in (("out", out, n * lq * m * d, value.dtype), ("grad_value", gv, value.numel(), value.dtype),
                                ("grad_loc", gl, sampling_locations.numel(), torch.float32),
                                ("grad_attn", ga, attention_weights.numel(), torch.float32)):
         if t.is_cuda or not t.is_contiguous() or t.numel() != numel or t.dtype != dt:
@@ -75,11 +75,11 @@ def host_step(value, spatial_shapes, level_start_index, sampling_locations, atte
                                f"got {tuple(t.shape)} {t.dtype} on {t.device}")
     is_bf16 = int(value.dtype == torch.bfloat16)
     need = int(_lib.lib.msda_host_step_workspace_bytes(is_bf16, s, m, d, nl, lq, p, int(images_per_chunk)))
-    ws = _workspace(dev, max(need, 256))
     fn = getattr(_lib.lib, "msda_host_step_" + _SUFFIX[value.dtype])
     ptr = lambda t: ctypes.c_void_p(t.data_ptr())
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream()
+        ws = _workspace(dev, stream.cuda_stream, max(need, 256))
         rc = fn(ptr(value), ptr(spatial_shapes), ptr(level_start_index), ptr(sampling_locations), ptr(attention_weights),
                 ptr(grad_output), ptr(out), ptr(gv), ptr(gl), ptr(ga), ptr(ws), ctypes.c_size_t(ws.numel()),
                 n, s, m, d, nl, lq, p, int(images_per_chunk), ctypes.c_void_p(stream.cuda_stream))

@@ -53,8 +53,8 @@ class MSDeformAttn(nn.Module):
             warnings.warn("You'd better set d_model in MSDeformAttn to make the dimension of each attention head "
                           "a power of 2 which is more efficient in our CUDA implementation.")
         self.im2col_step = 64                      # reference :87; kept for API parity (validated, not needed)
-        # fold softmax + "ref + offset / (W,H)" into the kernels when the call allows it
-        # (2-dim reference points that need no gradient -- the encoder); set False for the literal path
+        # fold softmax + the reference-point arithmetic into the kernels when the call allows it
+        # (all six MSDA calls of a MonoDETR training forward do); set False for the literal path
         self.fuse_preprocessing = True
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
         self.conditional = conditional
@@ -97,8 +97,12 @@ class MSDeformAttn(nn.Module):
         value = value.view(n, len_in, self.n_heads, value.shape[-1] // self.n_heads)
         offsets = self.sampling_offsets(query).view(n, len_q, self.n_heads, self.n_levels, self.n_points, 2)
         weights = self.attention_weights(query).view(n, len_q, self.n_heads, self.n_levels * self.n_points)
-        if (self.fuse_preprocessing and not reference_points.requires_grad
-                and fused_supported(value, reference_points, self.n_levels, self.n_points)):
+        # fused path: 2-dim reference points (with or without a gradient: encoder, decoder layer 0) and 6-dim ones
+        # that need no gradient (decoder layers 1+: the reference detaches them, depthaware_transformer.py:613)
+        if (self.fuse_preprocessing
+                and (reference_points.shape[-1] == 2 or not (reference_points.requires_grad and torch.is_grad_enabled()))
+                and fused_supported(value, reference_points, offsets, weights, input_spatial_shapes,
+                                    input_level_start_index, self.n_levels, self.n_points)):
             output = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                                      reference_points, offsets, weights)
             return self.output_proj(output)

@@ -23,7 +23,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in include/msda_b200.h but not exported"
     assert set(_lib.EXPORTS) == declared
-    assert _lib.lib.msda_abi_version() == 1
+    assert _lib.lib.msda_abi_version() == _lib.ABI_VERSION == 2
     assert "sm_100a" in _lib.build_info()
     assert monosowa_b200.MSDeformAttnFunction is not None
 
@@ -59,12 +59,25 @@ def test_argument_errors_are_reported_without_a_gpu():
     _lib.set_tuning("fwd_pipe", 6)
     assert _lib.get_tuning("fwd_pipe") == 6
     _lib.set_tuning("fwd_pipe", -1)
-    assert lib.msda_describe_forward(32, 0, 32, 4, 4) == b"fwd_rec_f32"
-    assert lib.msda_describe_backward(32, 0, 32, 4, 4) == b"bwd_rec_f32"
-    assert lib.msda_describe_backward(32, 0, 32, 4, 3) == b"bwd_rec_f32"
-    assert lib.msda_describe_backward(32, 1, 32, 4, 4) == b"bwd_rec_bf16"
-    assert lib.msda_describe_forward(64, 0, 32, 4, 4) == b"fwd_generic_f64"
-    assert lib.msda_describe_backward(32, 0, 30, 4, 4) == b"bwd_generic_f32"
+    assert lib.msda_describe_forward(32, 0, 16, 8, 32, 4, 4, 550) == b"fwd_rec_f32"
+    assert lib.msda_describe_backward(32, 0, 16, 8, 32, 4, 4, 550) == b"bwd_rec_f32"
+    assert lib.msda_describe_backward(32, 0, 16, 8, 32, 4, 3, 50) == b"bwd_rec_f32"
+    assert lib.msda_describe_backward(32, 1, 16, 8, 32, 4, 4, 50) == b"bwd_rec_bf16"
+    assert lib.msda_describe_forward(64, 0, 16, 8, 32, 4, 4, 10200) == b"fwd_generic_f64"
+    assert lib.msda_describe_backward(32, 0, 16, 8, 30, 4, 4, 10200) == b"bwd_generic_f32"
+    # long query sets (the encoder): the backward combines the coarse levels in shared memory (binned kernel) when
+    # there are enough (image, head, chunk) work items; the forward stays with the record kernel
+    assert lib.msda_describe_forward(32, 0, 16, 8, 32, 4, 4, 10200) == b"fwd_rec_f32"
+    assert lib.msda_describe_backward(32, 0, 16, 8, 32, 4, 4, 10200) == b"bwd_bin_f32"
+    assert lib.msda_describe_backward(32, 1, 16, 8, 32, 4, 4, 10200) == b"bwd_bin_bf16"
+    assert lib.msda_describe_backward(32, 0, 2, 8, 32, 4, 4, 10200) == b"bwd_rec_f32"       # too few work items
+    assert _lib.describe("backward", torch.bfloat16, 16, 8, 32, 4, 4, 550) == "bwd_rec_bf16"
+    # bf16 backward: short query sets scatter straight into the bf16 gradient, long ones need the fp32 scratch
+    assert lib.msda_backward_bf16_scratch_bytes(16, 10200, 8, 32, 4, 550, 4, 1) == 0
+    assert lib.msda_backward_bf16_scratch_bytes(1, 640, 8, 32, 4, 300, 4, 1) == 640 * 8 * 32 * 4      # dense: 30 additions per row
+    assert lib.msda_backward_bf16_scratch_bytes(2, 10200, 8, 32, 4, 10200, 4, 1) == 2 * 10200 * 8 * 32 * 4
+    assert lib.msda_backward_bf16_scratch_bytes(2, 100, 8, 30, 4, 50, 4, 1) == 2 * 100 * 8 * 30 * 4      # generic kernel
+    assert lib.msda_backward_bf16_scratch_bytes(2, 100, 8, 32, 4, 50, 4, 0) == 2 * 100 * 8 * 32 * 4      # misaligned
 
 
 def test_cpu_tensors_raise_not_implemented_no_fallback():

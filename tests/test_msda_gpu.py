@@ -190,32 +190,25 @@ def test_kernels_vs_oracle(msda, case, dtype):
     check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=str(case))
 
 
-@pytest.mark.parametrize("order", [10, 11, 99])
-def test_every_launch_variant_is_correct(msda, order):
-    """work order 0 / 1 of the record kernels and the generic kernels on a vectorisable shape"""
+def _needs_ab(msda):
+    if not msda._lib.has_ab_flavours():
+        pytest.skip("tile kernels exist only in the measurement build: MSDA_AB=1 pytest ... (python -m monosowa_b200.build --ab)")
+
+
+@pytest.mark.parametrize("variant", [(11, 11), (11, 21), (12, 20), (99, 99)], ids=["record", "binned", "tile", "generic"])
+def test_every_launch_variant_is_correct(msda, variant):
+    """record kernels, binned backward and tile kernels (forced for a short query set) and the generic kernels on a
+    vectorisable shape"""
+    if variant == (12, 20):
+        _needs_ab(msda)
     value, sh, lsi, loc, attn, grad_out = _random_case(7, [(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 203, 4)
     L = msda._lib
     try:
-        L.set_tuning("fwd_variant", order); L.set_tuning("bwd_variant", order)
-        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.float32, label=f"order{order}")
-        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.bfloat16, label=f"order{order}")
+        L.set_tuning("fwd_variant", variant[0]); L.set_tuning("bwd_variant", variant[1])
+        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.float32, label=f"variant{variant}")
+        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.bfloat16, label=f"variant{variant}")
     finally:
         L.set_tuning("fwd_variant", -1); L.set_tuning("bwd_variant", -1)
-
-
-@pytest.mark.parametrize("pipe", [3, 4, 5, 6, 14, 15, 16, 24, 25, 26, 27, 35, 36])
-def test_record_kernel_launch_flavours(msda, pipe):
-    """fwd_pipe / bwd_pipe select register caps and the compacting forward; all must agree with the oracle."""
-    L = msda._lib
-    try:
-        L.set_tuning("fwd_pipe", pipe); L.set_tuning("bwd_pipe", {3: 3, 4: 4, 5: 1, 6: 2, 25: 13, 35: 23}.get(pipe, -1))
-        for case in ([(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 203, 4), ([(9, 7), (5, 4), (3, 3)], 2, 4, 32, 19, 3):
-            shapes, N, M, D, Lq, P = case
-            value, sh, lsi, loc, attn, grad_out = _random_case(21, shapes, N, M, D, Lq, P)
-            for dtype in (torch.float32, torch.bfloat16):
-                check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=f"pipe{pipe} {case}")
-    finally:
-        L.set_tuning("fwd_pipe", -1); L.set_tuning("bwd_pipe", -1)
 
 
 def _fuzz_case(i):
@@ -251,94 +244,159 @@ def test_generic_and_record_kernels_agree(msda):
         assert O.rel_l2(x, y) < tol
 
 
-# --- binned backward (msda_backward_binned.cu): coarse levels combined in shared memory ---------------
-# bwd_variant 20 forces the kernel for any Lq (by default it serves Lq >= 1024); which levels are binned is
-# decided on the device: coarsest first while cells fit 704, samples per query fit 8 and H*W <= QC*P.
-BIN_CASES = [
-    # (shapes, N, M, D, Lq, P)
-    ([(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 300, 4),    # pyramid: levels 2 and 3 binned (8 samples); two chunks, ragged
-    ([(6, 4), (3, 2)], 1, 2, 32, 2, 2),                          # ops/test.py shape: every level binned
-    ([(9, 7), (5, 4), (3, 3)], 2, 4, 32, 519, 3),                # P = 3: two levels (6 samples), three chunks
-    ([(9, 7), (5, 4)], 2, 4, 16, 700, 8),                        # D = 16 (4-lane groups), P = 8: one level binned
-    ([(9, 7), (5, 4)], 2, 4, 64, 150, 4),                        # D = 64 (16-lane groups, 128-query chunks)
-    ([(16, 16)], 1, 1, 32, 257, 4),                              # single level, 289 cells, one query in the last chunk
-    ([(40, 40), (30, 30)], 1, 2, 32, 300, 4),                    # no level fits the cell budget: direct reductions only
-    ([(9, 7), (5, 4)], 2, 4, 32, 100, 16),                       # P = 16 exceeds the 8 entry slots: nothing binned
-    ([(9, 7), (1, 1)], 2, 3, 32, 260, 4),                        # 1x1 coarsest level: four cells, one hot row
-    ([(20, 25), (2, 2)], 1, 2, 32, 300, 4),                      # fine level too large for 704 cells -> only the 2x2 level
+# --- binned backward (msda_backward_binned.cu; the default for long query sets) and the tile kernels (msda_tiles.cuh,
+# fwd_tile_kernel, msda_backward_tiled.cu; measurement build only) ---------------------------------------------------
+# binned: chunks of 256 consecutive queries of one head; the grad_value contributions of the COARSE levels (decided on
+# the device: coarsest first while their cells fit 704 and their samples fit 8 per query) are combined in shared memory.
+# tile: a persistent grid over work items (image, head, tile).  When the queries ARE the pixel pyramid (Lq == sum H*W:
+# the encoder) a tile is a 12 x 16 block of the largest level plus the coarser levels' pixels of the same image region,
+# and the backward combines the contributions of EVERY level inside per-level windows (tile + 6 pixel halo); other
+# query sets run in chunks of consecutive queries with whole-level windows.  bwd_variant 21 / 20 force the binned / tile
+# backward for any Lq, fwd_variant 12 the tile forward.
+def _encoder_case(seed, shapes, N, M, D, P, sigma_px=2.0):
+    """queries = the pixel pyramid; locations = own pixel centre on every level + N(0, sigma_px) offsets
+    (SURVEY.md 8d 'model-like'): what MonoDETR's encoder produces (reference depthaware_transformer.py:363-376)"""
+    from monosowa_b200.workloads import encoder_reference_points
+    g = torch.Generator().manual_seed(seed)
+    sh, lsi = _levels(shapes)
+    S, L = int(sh.prod(1).sum()), len(shapes)
+    value = torch.randn(N, S, M, D, generator=g, dtype=torch.float64)
+    ref = encoder_reference_points(shapes, "cpu", torch.float64)[None].expand(N, -1, -1, -1)
+    wh = torch.stack([sh[:, 1], sh[:, 0]], -1).double()
+    off = torch.randn(N, S, M, L, P, 2, generator=g, dtype=torch.float64) * sigma_px
+    loc = (ref[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]).contiguous()
+    attn = torch.softmax(torch.randn(N, S, M, L * P, generator=g, dtype=torch.float64), -1).view(N, S, M, L, P)
+    grad_out = torch.randn(N, S, M * D, generator=g, dtype=torch.float64)
+    return value, sh, lsi, loc, attn, grad_out
+
+
+GRID_CASES = [
+    # (shapes, N, M, D, P, sigma_px)                                  queries = the pyramid (grid mode)
+    ([(24, 80), (12, 40), (6, 20), (3, 10)], 2, 8, 32, 4, 2.0),      # MonoDETR layout at half size: 2 x 5 tiles
+    ([(24, 80), (12, 40), (6, 20), (3, 10)], 1, 2, 32, 4, 9.0),      # large offsets: many samples leave the windows (strays)
+    ([(13, 37), (7, 19), (4, 10)], 2, 3, 32, 4, 2.0),                # not dyadic, ragged tiles, M = 3
+    ([(30, 30)], 1, 2, 32, 4, 1.5),                                  # a single level
+    ([(3, 10), (24, 80), (6, 20), (12, 40)], 1, 2, 32, 4, 2.0),      # levels not ordered by size: tiling base = level 1
+    ([(6, 4), (3, 2)], 1, 2, 32, 2, 1.0),                            # ops/test.py pyramid: one tile
+    ([(24, 40), (12, 20), (6, 10)], 2, 4, 16, 4, 2.0),               # D = 16: 4-lane groups, three batches of 4 samples
+    ([(24, 40), (12, 20)], 1, 2, 64, 4, 2.0),                        # D = 64: 16-lane groups, rounds of 128 queries
+    ([(24, 40), (12, 20), (6, 10)], 1, 4, 32, 3, 2.0),               # P = 3: batches straddle levels, ragged last batch
+    ([(20, 33), (10, 17)], 1, 2, 32, 16, 2.0),                       # P = 16: a level spans two batches
+    ([(40, 48), (40, 48), (40, 48)], 1, 1, 32, 4, 2.0),              # equal levels: 576 queries per tile -> three rounds
+]
+
+LINEAR_CASES = [
+    # (shapes, N, M, D, Lq, P)                                        queries are NOT the pyramid (linear mode)
+    ([(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 300, 4),        # coarse levels windowed whole; two chunks, ragged
+    ([(9, 7), (5, 4), (3, 3)], 2, 4, 32, 519, 3),                    # P = 3, three chunks
+    ([(9, 7), (5, 4)], 2, 4, 16, 700, 8),                            # D = 16, P = 8
+    ([(9, 7), (5, 4)], 2, 4, 64, 150, 4),                            # D = 64 (128-query chunks)
+    ([(16, 16)], 1, 1, 32, 257, 4),                                  # single level, one query in the last chunk
+    ([(40, 40), (30, 30)], 1, 2, 32, 300, 4),                        # no level fits the cell budget: direct reductions only
+    ([(9, 7), (1, 1)], 2, 3, 32, 260, 4),                            # 1x1 coarsest level: four cells, one hot row
+    ([(6, 4), (3, 2)], 1, 2, 32, 2, 2),                              # two queries
 ]
 
 
-@pytest.mark.parametrize("case", BIN_CASES, ids=lambda c: f"M{c[2]}D{c[3]}Lq{c[4]}P{c[5]}L{len(c[0])}")
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("variant", [20, 21, 23, 25])
-def test_binned_backward_vs_oracle_and_direct(msda, case, dtype, variant):
-    """the binned kernel against the fp64 oracle, and against the record kernel: grad_loc / grad_attn come from
-    identical arithmetic (bitwise equal), grad_value differs only in summation order."""
-    shapes, N, M, D, Lq, P = case
-    value, sh, lsi, loc, attn, grad_out = _random_case(300 + D + Lq, shapes, N, M, D, Lq, P, spread=1.4, shift=-0.2)
+def _tile_vs_oracle_and_record(msda, case_inputs, dtype, label, variants=(12, 20)):
+    """binned / tile kernels against the fp64 oracle, and against the record kernels: out, grad_loc and grad_attn come
+    from identical per-query arithmetic (bitwise equal), grad_value differs only in summation order."""
+    value, sh, lsi, loc, attn, grad_out = case_inputs
     L = msda._lib
     ct = torch.float32
     try:
-        L.set_tuning("bwd_variant", variant)
-        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=f"binned {case}")
+        L.set_tuning("fwd_variant", variants[0]); L.set_tuning("bwd_variant", variants[1])
+        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=label)
         b = run_ours(msda, value.to(dtype), sh, lsi, loc.to(ct), attn.to(ct), grad_out.to(dtype))
-        L.set_tuning("bwd_variant", 11)
+        L.set_tuning("fwd_variant", 11); L.set_tuning("bwd_variant", 11)
         a = run_ours(msda, value.to(dtype), sh, lsi, loc.to(ct), attn.to(ct), grad_out.to(dtype))
     finally:
-        L.set_tuning("bwd_variant", -1)
-    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+        L.set_tuning("fwd_variant", -1); L.set_tuning("bwd_variant", -1)
+    assert torch.equal(a[0], b[0]), "forward differs from the record kernel"
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]), "grad_loc / grad_attn differ from the record kernel"
     assert O.rel_l2(b[1], a[1]) < (1e-5 if dtype == torch.float32 else 1e-2)
 
 
+KERNEL_FAMILIES = [pytest.param((11, 21), id="binned"), pytest.param((12, 20), id="tile")]
+
+
+@pytest.mark.parametrize("variants", KERNEL_FAMILIES)
+@pytest.mark.parametrize("case", GRID_CASES, ids=lambda c: f"M{c[2]}D{c[3]}P{c[4]}L{len(c[0])}s{c[5]}")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_long_query_kernels_on_pixel_pyramids(msda, case, dtype, variants):
+    if variants[1] == 20:
+        _needs_ab(msda)
+    shapes, N, M, D, P, sigma = case
+    _tile_vs_oracle_and_record(msda, _encoder_case(700 + D + P, shapes, N, M, D, P, sigma), dtype, f"grid {case}", variants)
+
+
+@pytest.mark.parametrize("variants", KERNEL_FAMILIES)
+@pytest.mark.parametrize("case", LINEAR_CASES, ids=lambda c: f"M{c[2]}D{c[3]}Lq{c[4]}P{c[5]}L{len(c[0])}")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_long_query_kernels_on_arbitrary_query_sets(msda, case, dtype, variants):
+    if variants[1] == 20:
+        _needs_ab(msda)
+    shapes, N, M, D, Lq, P = case
+    inputs = _random_case(300 + D + Lq, shapes, N, M, D, Lq, P, spread=1.4, shift=-0.2)
+    _tile_vs_oracle_and_record(msda, inputs, dtype, f"linear {case}", variants)
+
+
+@pytest.mark.parametrize("variants", KERNEL_FAMILIES)
+def test_long_query_kernels_uniform_locations_on_a_pyramid(msda, variants):
+    """locations that ignore the query's own position: for the tile kernel nearly every fine-level sample is a stray"""
+    if variants[1] == 20:
+        _needs_ab(msda)
+    shapes = [(24, 80), (12, 40), (6, 20), (3, 10)]
+    S = sum(h * w for h, w in shapes)
+    inputs = _random_case(811, shapes, 1, 4, 32, S, 4, spread=1.3, shift=-0.15)
+    _tile_vs_oracle_and_record(msda, inputs, torch.float32, "uniform on pyramid", variants)
+
+
 def test_binned_backward_is_the_default_for_long_query_sets(msda, cuda_device):
-    """Lq >= 1024 takes the binned kernel without any tuning; hot coarse pixels (every query samples the same
-    corner of the coarsest level) stress the per-cell counters: 2048 entries in one cell."""
-    shapes, N, M, D, Lq, P = [(12, 40), (6, 20), (3, 10), (2, 5)], 1, 2, 32, 1100, 4
+    """Lq >= 1024 with enough (image, head, chunk) work items takes the binned kernel without any tuning; hot coarse
+    pixels (every query samples the same corner of the coarsest levels) stress the per-cell counters: 2048 entries in
+    one cell."""
+    assert msda._lib.describe("forward", torch.float32, 16, 8, 32, 4, 4, 10200) == "fwd_rec_f32"
+    assert msda._lib.describe("backward", torch.float32, 16, 8, 32, 4, 4, 10200) == "bwd_bin_f32"
+    assert msda._lib.describe("backward", torch.float32, 16, 8, 32, 4, 4, 550) == "bwd_rec_f32"
+    shapes, N, M, D, Lq, P = [(12, 40), (6, 20), (3, 10), (2, 5)], 16, 40, 32, 1100, 4
+    assert msda._lib.describe("backward", torch.float32, N, M, D, len(shapes), P, Lq) == "bwd_bin_f32"
     value, sh, lsi, loc, attn, grad_out = _random_case(41, shapes, N, M, D, Lq, P, spread=1.2, shift=-0.1)
     loc[:, :, :, 2:, :, :] = 0.26                                 # all coarse samples in one cell
     check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, torch.float32, label="hot cell")
     L = msda._lib
     a = run_ours(msda, value.float(), sh, lsi, loc.float(), attn.float(), grad_out.float())
     try:
-        L.set_tuning("bwd_variant", 11)
+        L.set_tuning("fwd_variant", 11); L.set_tuning("bwd_variant", 11)
         b = run_ours(msda, value.float(), sh, lsi, loc.float(), attn.float(), grad_out.float())
     finally:
-        L.set_tuning("bwd_variant", -1)
-    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and O.rel_l2(a[1], b[1]) < 1e-5
+        L.set_tuning("fwd_variant", -1); L.set_tuning("bwd_variant", -1)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and O.rel_l2(a[1], b[1]) < 1e-5
 
 
-# --- resident forward (msda_forward_resident.cu): coarse levels copied into shared memory per CTA ------------
-RES_CASES = [
-    # (shapes, N, M, D, Lq, P)
-    ([(48, 160), (24, 80), (12, 40), (6, 20)], 1, 2, 32, 1300, 4),   # KITTI pyramid: levels 2, 3 resident (77 KB fp32), two chunks
-    ([(12, 40), (6, 20), (3, 10), (2, 5)], 2, 8, 32, 300, 4),        # every level fits: all gathers from shared memory
-    ([(160, 240), (9, 7)], 1, 2, 32, 200, 4),                        # fine level far too large: only the coarse one resident
-    ([(200, 200)], 1, 1, 32, 100, 4),                                # nothing fits: plain global gathers
-    ([(9, 7), (5, 4), (3, 3)], 2, 4, 16, 1100, 3),                   # D = 16, ragged batches
-    ([(9, 7), (5, 4)], 2, 4, 64, 70, 4),                             # D = 64
-    ([(30, 30), (9, 7), (1, 1)], 2, 3, 32, 1025, 4),                 # one query in the second chunk
-]
-
-
-@pytest.mark.parametrize("case", RES_CASES, ids=lambda c: f"M{c[2]}D{c[3]}Lq{c[4]}P{c[5]}L{len(c[0])}")
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_resident_forward_vs_oracle_and_record_kernel(msda, case, dtype):
-    """fwd_variant 30 forces the resident kernel for any Lq: against the fp64 oracle, and bitwise against the record
-    kernel (same arithmetic and accumulation order; only where the rows are read from differs)."""
-    shapes, N, M, D, Lq, P = case
-    value, sh, lsi, loc, attn, grad_out = _random_case(500 + D + Lq, shapes, N, M, D, Lq, P, spread=1.4, shift=-0.2)
-    L = msda._lib
-    try:
-        L.set_tuning("fwd_variant", 30)
-        check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=f"resident {case}")
-        b = run_ours(msda, value.to(dtype), sh, lsi, loc.float(), attn.float(), grad_out.to(dtype))
-        L.set_tuning("fwd_variant", 11)
-        L.set_tuning("fwd_pipe", 25)                                   # the compacting record kernel
-        a = run_ours(msda, value.to(dtype), sh, lsi, loc.float(), attn.float(), grad_out.to(dtype))
-    finally:
-        L.set_tuning("fwd_variant", -1); L.set_tuning("fwd_pipe", -1)
-    assert torch.equal(a[0], b[0])
+def test_nan_behind_outside_samples_does_not_leak(msda, cuda_device):
+    """The reference never touches `value` for a sample outside the (-1,H)x(-1,W) window (cuh:288).  Neither do
+    these kernels: a NaN in pixel 0 of every head and level must not reach queries whose samples there are outside."""
+    shapes, N, M, D, Lq, P = [(6, 8), (3, 4)], 1, 2, 32, 40, 4
+    value, sh, lsi, loc, attn, grad_out = _random_case(97, shapes, N, M, D, Lq, P, spread=0.5, shift=0.3)
+    loc[:, ::2, :, :, 0] = 1.7                                     # every second query: one sample per level far outside
+    for dtype in (torch.float32, torch.bfloat16):
+        v = value.to(dtype).clone()
+        clean = run_ours(msda, v, sh, lsi, loc.float(), attn.float(), grad_out.to(dtype))
+        v[:, 0] = float("nan"); v[:, int(lsi[1])] = float("nan")   # pixel (0,0) of both levels
+        for fv, bv in ((11, 11), (11, 21)) + (((12, 20),) if msda._lib.has_ab_flavours() else ()):
+            msda._lib.set_tuning("fwd_variant", fv); msda._lib.set_tuning("bwd_variant", bv)
+            try:
+                got = run_ours(msda, v, sh, lsi, loc.float(), attn.float(), grad_out.to(dtype))
+            finally:
+                msda._lib.set_tuning("fwd_variant", -1); msda._lib.set_tuning("bwd_variant", -1)
+            # locations in [0.3, 0.8] never touch pixel (0,0) with a non-zero weight... unless a corner is pixel 0:
+            touches = torch.isnan(got[0]).reshape(N, Lq, -1).any(-1)
+            ref_touch = torch.isnan(O.forward_c(v.double(), sh, lsi, loc, attn)).reshape(N, Lq, -1).any(-1)
+            assert torch.equal(touches, ref_touch), f"NaN pattern differs from the oracle ({dtype}, variants {fv}/{bv})"
+            ok = ~ref_touch
+            assert torch.equal(got[0][ok], clean[0][ok])
+            assert torch.isfinite(got[2][ok]).all() and torch.isfinite(got[3][ok]).all()
 
 
 def test_edge_locations_exact_borders(msda):
@@ -431,16 +489,21 @@ def test_config1_full_size_f32(msda, cuda_device, mode):
 def test_config2_decoder_bf16(msda, lq):
     """configs[2]: decoder cross-attention, 50 (eval) / 550 (train) queries, bf16 value."""
     from monosowa_b200 import workloads as W
-    wl = W.config(2, num_queries=lq, batch=4)
+    wl = W.config(2, num_queries=lq)                       # batch 16, as BASELINE.json states
     d = W.make_inputs(wl)
-    check_against_oracle(msda, d["value"].double(), d["shapes"], d["lsi"], d["loc"].double(), d["attn"].double(),
-                         d["grad_out"].double(), torch.bfloat16, label=wl.name)
+    # short query sets scatter straight into the bf16 gradient (REDG.E.ADD.BF16x4, no fp32 buffer, no narrowing pass)
+    assert msda._lib.lib.msda_backward_bf16_scratch_bytes(wl.batch, wl.S, wl.heads, wl.head_dim, wl.L, lq, wl.points, 1) == 0
+    e = check_against_oracle(msda, d["value"].double(), d["shapes"], d["lsi"], d["loc"].double(), d["attn"].double(),
+                             d["grad_out"].double(), torch.bfloat16, label=wl.name)
+    print(f"config2 Lq={lq} bf16 errors {e}")
+    assert e["gv"] < 8e-3, "per-addition bf16 rounding of grad_value must stay inside the 1e-2 contract (measured 5.3e-3 at Lq=550)"
 
 
 def test_config4_large_image_shapes(msda):
-    """configs[4] shapes (KITTI-360, Waymo 1280x1920, 640x960), batch 1, fp32 + bf16."""
+    """configs[4] shapes (KITTI-360, Waymo 1280x1920, 640x960), batch 4 as SURVEY.md 8d states, fp32 + bf16
+    (the C oracle needs about a minute for the Waymo shape)."""
     from monosowa_b200 import workloads as W
-    for wl in W.sweep_config5(batch=1):
+    for wl in W.sweep_config5(batch=4):
         d = W.make_inputs(wl)
         check_against_oracle(msda, d["value"].double(), d["shapes"], d["lsi"], d["loc"].double(),
                              d["attn"].double(), d["grad_out"].double(), wl.dtype, label=wl.name)
@@ -467,7 +530,7 @@ def test_beyond_int32_indexing(msda, cuda_device):
     attn = torch.softmax(torch.randn(1, Lq, M, 2 * P, generator=g, device=dev), -1).view(1, Lq, M, 2, P).requires_grad_(True)
     grad_out = torch.randn(1, Lq, M * D, generator=g, device=dev)
     v = value.requires_grad_(True)
-    assert msda._lib.lib.msda_describe_forward(32, 0, D, 2, P) == b"fwd_rec_f32"     # the shape alone would vectorise
+    assert msda._lib.describe("forward", torch.float32, 1, M, D, 2, P, Lq) == "fwd_rec_f32"   # the shape alone would vectorise
     out = msda.MSDeformAttnFunction.apply(v, sh, lsi, loc, attn, 64)
     out.backward(grad_out)
     torch.cuda.synchronize()
@@ -569,8 +632,10 @@ def test_c_abi_direct_call_and_error_codes(msda, cuda_device):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
 @pytest.mark.parametrize("shape", [([(5, 7), (3, 4), (1, 1)], 2, 8, 32, 37, 4), ([(4, 3)], 1, 3, 16, 9, 2), ([(6, 5), (2, 2)], 1, 2, 24, 5, 3)])
-@pytest.mark.parametrize("bwd_variant", [-1, 20])
+@pytest.mark.parametrize("bwd_variant", [-1, 21, 20])
 def test_guard_bands_no_out_of_bounds_access(msda, cuda_device, dtype, shape, bwd_variant):
+    if bwd_variant == 20:
+        _needs_ab(msda)
     msda._lib.set_tuning("bwd_variant", bwd_variant)
     try:
         _guard_bands(msda, cuda_device, dtype, shape)
@@ -589,7 +654,7 @@ def _guard_bands(msda, cuda_device, dtype, shape):
     pick = torch.randint(0, len(border), loc.shape, generator=torch.Generator().manual_seed(5))
     loc = torch.where(torch.rand(loc.shape, generator=torch.Generator().manual_seed(6)) < 0.5, border[pick], loc)
     dev, ct = cuda_device, (torch.float64 if dtype == torch.float64 else torch.float32)
-    gvt = ct                                                       # grad_value accumulates in fp32 / fp64
+    gvt = dtype                                                    # grad_value has value's dtype
     GUARD = 4096                                                   # elements on each side
 
     def carve(t, fill):
@@ -617,8 +682,14 @@ def _guard_bands(msda, cuda_device, dtype, shape):
     rc = getattr(lib, "msda_forward_" + sfx)(p(views["value"]), p(shd), p(lsid), p(views["loc"]), p(views["attn"]),
                                              p(views["out"]), N, S, M, D, L, Lq, P, st)
     assert rc == 0, msda._lib.last_error()
+    extra = []
+    if dtype == torch.bfloat16:                                    # fp32 accumulation buffer, when this shape needs one
+        nb = lib.msda_backward_bf16_scratch_bytes(N, S, M, D, L, Lq, P, 0)     # 0: the carved views are only 4-byte aligned
+        outs["scratch"] = torch.empty(max(nb // 4, 1), dtype=torch.float32)
+        bufs["scratch"], views["scratch"] = carve(outs["scratch"].to(dev), SENT)
+        extra = [p(views["scratch"])]
     rc = getattr(lib, "msda_backward_" + sfx)(p(views["value"]), p(shd), p(lsid), p(views["loc"]), p(views["attn"]),
-                                              p(views["grad_out"]), p(views["gv"]), p(views["gl"]), p(views["ga"]),
+                                              p(views["grad_out"]), p(views["gv"]), p(views["gl"]), p(views["ga"]), *extra,
                                               N, S, M, D, L, Lq, P, st)
     assert rc == 0, msda._lib.last_error()
     torch.cuda.synchronize()
@@ -630,7 +701,7 @@ def _guard_bands(msda, cuda_device, dtype, shape):
     tol = TOL[dtype]
     assert O.rel_l2(views["out"], O.forward_c(*args)) <= tol["fwd"]
     rgv, rgl, rga = O.backward_c(*args, ins["grad_out"].double())
-    assert O.rel_l2(views["gv"], rgv) <= (1e-4 if dtype == torch.bfloat16 else tol["gv"])   # fp32 accumulator here
+    assert O.rel_l2(views["gv"], rgv) <= tol["gv"]
     assert O.rel_l2(views["ga"], rga) <= tol["ga"]
 
 
@@ -648,7 +719,7 @@ def test_host_buffer_step_matches_device_path(msda, cuda_device, dtype, per_chun
     dev = cuda_device
     out, gv, gl, ga = msda.host_step(v.pin_memory(), sh.to(dev), lsi.to(dev), l.pin_memory(), a.pin_memory(),
                                      g.reshape(N, Lq, M * D).pin_memory(), images_per_chunk=per_chunk)
-    assert not out.is_cuda and out.dtype == dtype and gv.dtype == torch.float32
+    assert not out.is_cuda and out.dtype == dtype and gv.dtype == dtype
     assert torch.equal(out, want[0]) and torch.equal(gl, want[2]) and torch.equal(ga, want[3])
     assert O.rel_l2(gv, want[1]) < (1e-5 if dtype == torch.float32 else 1e-2)
     # a second call reuses the cached workspace and the caller's result buffers
@@ -718,60 +789,111 @@ FUSED_CASES = [
 
 @pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: f"M{c[2]}D{c[3]}Lq{c[4]}P{c[5]}L{len(c[0])}")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("bwd_variant", [-1, 20])
-def test_fused_preprocessing_matches_unfused_and_oracle(msda, cuda_device, case, dtype, bwd_variant):
-    """bwd_variant 20: the fused flavours of the binned backward and (fwd_variant 30) of the resident forward"""
-    msda._lib.set_tuning("bwd_variant", bwd_variant)
-    msda._lib.set_tuning("fwd_variant", 30 if bwd_variant == 20 else -1)
+@pytest.mark.parametrize("family", [(11, 11), (11, 21), (12, 20)], ids=["record", "binned", "tile"])
+@pytest.mark.parametrize("ref_dim", [2, 6])
+def test_fused_preprocessing_matches_unfused_and_oracle(msda, cuda_device, case, dtype, family, ref_dim):
+    """the fused flavours of the record kernels, the binned backward and (measurement build) the tile kernels, with
+    2- and 6-dim reference points"""
+    if family == (12, 20):
+        _needs_ab(msda)
+    msda._lib.set_tuning("fwd_variant", family[0])
+    msda._lib.set_tuning("bwd_variant", family[1])
     try:
-        _fused_vs_unfused(msda, cuda_device, case, dtype)
+        _fused_vs_unfused(msda, cuda_device, case, dtype, ref_dim)
     finally:
         msda._lib.set_tuning("bwd_variant", -1); msda._lib.set_tuning("fwd_variant", -1)
 
 
-def _fused_vs_unfused(msda, cuda_device, case, dtype):
+@pytest.mark.parametrize("family", [(-1, -1), (11, 21), (12, 20)], ids=["default", "binned", "tile"])
+def test_fused_preprocessing_on_the_encoder_pyramid(msda, cuda_device, family):
+    """the encoder's call: queries = the pixel pyramid, reference points = pixel centres"""
+    from monosowa_b200.workloads import encoder_reference_points
+    if family == (12, 20):
+        _needs_ab(msda)
+    shapes = [(24, 80), (12, 40), (6, 20), (3, 10)]
+    S = sum(h * w for h, w in shapes)
+    ref = encoder_reference_points(shapes, cuda_device)[None].expand(2, -1, -1, -1).contiguous()
+    msda._lib.set_tuning("fwd_variant", family[0]); msda._lib.set_tuning("bwd_variant", family[1])
+    try:
+        for dtype in (torch.float32, torch.bfloat16):
+            _fused_vs_unfused(msda, cuda_device, (shapes, 2, 8, 32, S, 4), dtype, 2, ref=ref, off_sigma=2.0)
+    finally:
+        msda._lib.set_tuning("fwd_variant", -1); msda._lib.set_tuning("bwd_variant", -1)
+
+
+def _fused_vs_unfused(msda, cuda_device, case, dtype, ref_dim=2, ref=None, off_sigma=3.0):
     from monosowa_b200.ops.functions import MSDeformAttnFusedFunction, fused_supported
+    from monosowa_b200.ops.modules.ms_deform_attn import sampling_locations_from_reference
     shapes, N, M, D, Lq, P = case
     dev = cuda_device
     g = torch.Generator().manual_seed(77 + D + Lq)
     sh, lsi = _levels(shapes)
     S, L = int(sh.prod(1).sum()), len(shapes)
     value = torch.randn(N, S, M, D, generator=g).to(dev, dtype)
-    ref = (torch.rand(N, Lq, L, 2, generator=g) * 1.2 - 0.1).to(dev)
-    offs = (torch.randn(N, Lq, M, L, P, 2, generator=g) * 3.0).to(dev)
+    if ref is None:
+        ref = (torch.rand(N, Lq, L, 2, generator=g) * 1.2 - 0.1).to(dev)
+        if ref_dim == 6:                                      # (cx, cy, l, r, t, b): box extents of a few percent of the image
+            ref = torch.cat([ref, (torch.rand(N, Lq, L, 4, generator=g) * 0.3 + 0.02).to(dev)], -1)
+    offs = (torch.randn(N, Lq, M, L, P, 2, generator=g) * off_sigma).to(dev)
     logits = (torch.randn(N, Lq, M, L * P, generator=g) * 2.0).to(dev)
     grad_out = torch.randn(N, Lq, M * D, generator=g).to(dev, dtype)
     shd, lsid = sh.to(dev), lsi.to(dev)
-    assert fused_supported(value, ref, L, P)
+    assert fused_supported(value, ref, offs, logits, shd, lsid, L, P)
+    assert not fused_supported(value, ref.cpu(), offs, logits, shd, lsid, L, P)          # wrong device -> literal path
+    assert not fused_supported(value, ref, offs, logits, shd.int(), lsid, L, P)           # int32 shapes -> literal path
+    want_ref_grad = ref_dim == 2
 
-    def unfused(v, o, lg):
-        wh = torch.stack([shd[:, 1], shd[:, 0]], -1)
-        loc = ref[:, :, None, :, None, :] + o / wh[None, None, None, :, None, :]
+    def unfused(v, o, lg, r):
+        loc = sampling_locations_from_reference(r, o, shd, P)
         aw = torch.softmax(lg, -1).view(N, Lq, M, L, P)
         return msda.MSDeformAttnFunction.apply(v, shd, lsid, loc.contiguous(), aw.contiguous(), 64), loc, aw
 
     res = []
     for fused in (True, False):
         v = value.clone().requires_grad_(True); o = offs.clone().requires_grad_(True); lg = logits.clone().requires_grad_(True)
+        r = ref.clone().requires_grad_(want_ref_grad)
         if fused:
-            out = MSDeformAttnFusedFunction.apply(v, shd, lsid, ref, o, lg)
+            out = MSDeformAttnFusedFunction.apply(v, shd, lsid, r, o, lg)
         else:
-            out, loc, aw = unfused(v, o, lg)
+            out, loc, aw = unfused(v, o, lg, r)
         out.backward(grad_out)
-        res.append((out.detach(), v.grad, o.grad, lg.grad))
-    (fo, fgv, fgo, fgl), (uo, ugv, ugo, ugl) = res
+        res.append((out.detach(), v.grad, o.grad, lg.grad, r.grad))
+    (fo, fgv, fgo, fgl, fgr), (uo, ugv, ugo, ugl, ugr) = res
     t_out, t_gv = (2e-6, 1e-5) if dtype == torch.float32 else (4e-3, 1e-2)
+    assert fgv.dtype == dtype
     assert O.rel_l2(fo, uo) < t_out
     assert O.rel_l2(fgv, ugv) < t_gv
     assert O.rel_l2(fgl, ugl) < 1e-5
     # offsets: same floor() decisions (identical fp32 location arithmetic), so no masking needed
     assert O.rel_l2(fgo, ugo) < 1e-5
-    # and against the fp64 oracle on the locations / weights torch produced
-    ref_out = O.forward_c(value.cpu().double(), sh, lsi, loc.detach().cpu().double(), aw.detach().cpu().double())
+    if want_ref_grad:
+        assert O.rel_l2(fgr, ugr) < 1e-5
+    # and DIRECTLY against the fp64 oracle on the locations / weights torch produced (fp32-exact inputs)
+    loc64, aw64 = loc.detach().cpu().double(), aw.detach().cpu().double()
+    ref_out = O.forward_c(value.cpu().double(), sh, lsi, loc64, aw64)
     assert O.rel_l2(fo, ref_out) < (1e-5 if dtype == torch.float32 else 4e-3)
+    rgv, rgl, rga = O.backward_c(value.cpu().double(), sh, lsi, loc64, aw64, grad_out.cpu().double())
+    assert O.rel_l2(fgv, rgv) < (1e-4 if dtype == torch.float32 else 1e-2)
+    # chain rule through the pre-processing in fp64: softmax backward, d loc / d offset
+    rg_logit = (aw64 * (rga - (aw64 * rga).sum((-1, -2), keepdim=True))).reshape(N, Lq, M, L * P)
+    assert O.rel_l2(fgl, rg_logit) < 1e-4
+    if ref_dim == 2:
+        scale = 1.0 / torch.stack([sh[:, 1], sh[:, 0]], -1).double()[None, None, None, :, None, :]
+    else:
+        r64 = ref.cpu().double()[:, :, None, :, None, :]
+        scale = (r64[..., 2::2] + r64[..., 3::2]) * 0.5 / P
+    keep = ~O.pixel_boundary_mask(loc.detach().cpu(), sh, eps_px=1e-4)
+    assert O.rel_l2(fgo.cpu().double()[keep], (rgl * scale)[keep]) < 1e-4
+    if want_ref_grad:
+        rgl_m = torch.where(keep, rgl, torch.zeros_like(rgl))
+        fgl_back = torch.where(keep, fgo.cpu().double() / scale, torch.zeros_like(rgl))
+        assert O.rel_l2(fgl_back.sum((2, 4)), rgl_m.sum((2, 4))) < 1e-4
 
 
-def test_module_takes_the_fused_path_only_when_allowed(msda, cuda_device, monkeypatch):
+def test_module_takes_the_fused_path_for_every_call_of_a_training_forward(msda, cuda_device, monkeypatch):
+    """All six MSDA calls of a MonoDETR training forward qualify: the encoder (2-dim pixel-centre references, no
+    gradient), decoder layer 0 (2-dim learned references WITH a gradient, depthaware_transformer.py:286) and decoder
+    layers 1-2 (6-dim detached boxes, :613).  6-dim references that need a gradient, or wrong devices, stay literal."""
     from monosowa_b200.ops.modules import ms_deform_attn as modfile
     calls = []
     real_f, real_u = modfile.MSDeformAttnFusedFunction.apply, modfile.MSDeformAttnFunction.apply
@@ -789,14 +911,19 @@ def test_module_takes_the_fused_path_only_when_allowed(msda, cuda_device, monkey
     mod = msda.MSDeformAttn(64, 2, 4, 2).to(dev)
     q, src = torch.randn(2, 7, 64, device=dev), torch.randn(2, 60, 64, device=dev)
     ref2 = torch.rand(2, 7, 2, 2, device=dev)
+    ref6 = torch.cat([ref2, torch.rand(2, 7, 2, 4, device=dev) * 0.3], -1)
     out_f = mod(q, ref2, src, sh.to(dev), lsi.to(dev))
     mod.fuse_preprocessing = False
     out_u = mod(q, ref2, src, sh.to(dev), lsi.to(dev))
+    out6_u = mod(q, ref6, src, sh.to(dev), lsi.to(dev))
     mod.fuse_preprocessing = True
-    mod(q, ref2.clone().requires_grad_(True), src, sh.to(dev), lsi.to(dev))        # needs d/d ref -> unfused
-    mod(q, torch.rand(2, 7, 2, 6, device=dev) * 0.3, src, sh.to(dev), lsi.to(dev))  # 6-dim refs -> unfused
-    assert calls == ["fused", "unfused", "unfused", "unfused"]
-    assert O.rel_l2(out_f, out_u) < 2e-6
+    r2g = ref2.clone().requires_grad_(True)
+    mod(q, r2g, src, sh.to(dev), lsi.to(dev)).sum().backward()                        # 2-dim refs with a gradient -> fused
+    assert r2g.grad is not None and torch.isfinite(r2g.grad).all()
+    out6_f = mod(q, ref6, src, sh.to(dev), lsi.to(dev))                               # 6-dim detached refs -> fused
+    mod(q, ref6.clone().requires_grad_(True), src, sh.to(dev), lsi.to(dev))           # 6-dim refs with a gradient -> literal
+    assert calls == ["fused", "unfused", "unfused", "fused", "fused", "unfused"]
+    assert O.rel_l2(out_f, out_u) < 2e-6 and O.rel_l2(out6_f, out6_u) < 2e-6
 
 
 # --------------------------------------------------------------------------------------------

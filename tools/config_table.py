@@ -33,8 +33,8 @@ def main():
             bwd_GBps=round(ab["bwd"] / b / 1e6, 1), total_GBps=round(ab["total"] / (f + b) / 1e6, 1),
             frac_of_measured_hbm=round(ab["total"] / (f + b) / 1e6 / 6559.4, 4),
             alg_MB=round(ab["total"] / 1e6, 1),
-            kernels=[lib.msda_describe_forward(32, int(bf), wl.head_dim, wl.L, wl.points).decode(),
-                     lib.msda_describe_backward_lq(32, int(bf), wl.head_dim, wl.L, wl.points, wl.Lq).decode()])), flush=True)
+            kernels=[msda._lib.describe("forward", wl.dtype, wl.batch, wl.heads, wl.head_dim, wl.L, wl.points, wl.Lq),
+                     msda._lib.describe("backward", wl.dtype, wl.batch, wl.heads, wl.head_dim, wl.L, wl.points, wl.Lq)])), flush=True)
         del d, a5
         torch.cuda.empty_cache()
 
