@@ -189,8 +189,6 @@ def run_ours(args, wl):
         msda._lib.set_tuning(k_, int(v_))
     use_dist = world > 1
     if use_dist:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # keeps stdout to the one JSON line
-            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -349,6 +347,18 @@ def run_ours(args, wl):
     e2e_value, e2e_ms_max = aggregate(ab["total"], e2e_ms, world, reduce_fn if use_dist else None)
     chk = chk and (torch.equal(host_out[0].to(dev), out) if rank == 0 else True)   # both e2e paths reproduce the device forward
 
+    ref_cuda = time_reference_cuda(d, ab, args) if (world == 1 and rank == 0 and not args.no_ref_cuda) else None
+
+    # ---- the second half of BASELINE.json's metric: the MonoDETR training step (configs[3]) on the same ranks ------
+    kernels = {"fwd": msda._lib.describe("forward", wl.dtype, wl.batch, wl.heads, wl.head_dim, wl.L, wl.points, wl.Lq),
+               "bwd": msda._lib.describe("backward", wl.dtype, wl.batch, wl.heads, wl.head_dim, wl.L, wl.points, wl.Lq)}
+    out_shape_checked = bool(chk)
+    del d, a5, out, grads, host_in, dev_in, host_out, go_host, step_device, step_e2e, step_host, fwd_op, bwd_op, copy_rate, time_e2e
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    train = None if args.no_train_step else train_step_section(args, rank, world)
+
     if rank != 0:
         if use_dist:
             dist.destroy_process_group()
@@ -366,14 +376,13 @@ def run_ours(args, wl):
         "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
         "fwd_GBps": ab["fwd"] / (fwd_ms * 1e-3) / 1e9, "bwd_GBps": ab["bwd"] / (bwd_ms * 1e-3) / 1e9,
         "algorithmic_bytes": {"fwd": ab["fwd"], "bwd": ab["bwd"], "gather_cache_level": ab["gather"]},
-        "kernels": {"fwd": msda._lib.describe("forward", wl.dtype, wl.batch, wl.heads, wl.head_dim, wl.L, wl.points, wl.Lq),
-                    "bwd": msda._lib.describe("backward", wl.dtype, wl.batch, wl.heads, wl.head_dim, wl.L, wl.points, wl.Lq)},
+        "kernels": kernels,
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": load_traffic(dom[0]), "peak_source": peak_src,
                      "note": "achieved = algorithmic bytes of the launch / CUDA-event time on the launch stream; "
                              "bwd includes its cudaMemsetAsync of grad_value"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_max, "h2d_bytes_per_step": h2d_bytes * world,
-                "d2h_bytes_per_step": d2h_bytes * world, "bytes_note": "whole job (all ranks), like `value`", "chunks": chunks, "matches_device_path": bool(chk), "pcie": pcie,
+                "d2h_bytes_per_step": d2h_bytes * world, "bytes_note": "whole job (all ranks), like `value`", "chunks": chunks, "matches_device_path": out_shape_checked, "pcie": pcie,
                 "api": "msda_host_step_f32 (C ABI, pinned host buffers in and out; monosowa_b200.host_step), "
                        f"{args.e2e_images_per_chunk} image(s) per pipeline chunk",
                 "autograd_api_ms_per_step": e2e_autograd_ms,
@@ -381,6 +390,7 @@ def run_ours(args, wl):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "lib": msda._lib.build_info(),
+        "train_step": train,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -389,11 +399,59 @@ def run_ours(args, wl):
         ms = time_cpu(step, args.cpu_steps, 1)
         line["cpu_baseline"] = {"value": nbytes / (ms * 1e-3) / 1e9, "unit": UNIT, "cores": torch.get_num_threads(),
                                 "kind": "port", "sample": sample + f", {args.cpu_steps} timed steps", "ms_per_step": ms}
-    if world == 1 and not args.no_ref_cuda:
-        line["ref_cuda_kernel"] = time_reference_cuda(d, ab, args)
+    if ref_cuda is not None:
+        line["ref_cuda_kernel"] = ref_cuda
     print(json.dumps(line), flush=True)
     if use_dist:
         dist.destroy_process_group()
+
+
+def train_step_section(args, rank, world):
+    """BASELINE.json configs[3] through tools/train_step_bench.py on the ranks this process group already has:
+    the unmodified reference MonoDETR (staged under baseline/_ref) + SetCriterion + AdamW, DDP over NCCL, with this
+    repo's op and device-resident host sections.  At one GPU the same step is also timed with the reference's own
+    CUDA kernels (oracle/_ref) in a child process.  Returns a dict on rank 0 (None elsewhere); never raises."""
+    try:
+        from tools import train_step_bench as T
+        if not os.path.isdir(T.REF):
+            return {"unavailable": f"{T.REF} not staged (python tools/stage_reference.py where /root/reference exists)"} if rank == 0 else None
+        res = T.run(T.default_args(steps=args.train_steps, warmup=args.train_warmup, batch=16, op="ours", host_opt="all",
+                                   profile_msda=(world == 1), breakdown=(world == 1)))
+        if rank != 0:
+            return None
+        out = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": res["n_gpus"],
+               "ms_per_step": res["ms_per_step"], "ms_per_step_median": res["ms_per_step_median"], "steps": res["steps"],
+               "warmup": res["warmup"], "batch_per_gpu": 16, "global_batch": 16 * world, "scaling": "weak",
+               "parallelism": res["config"]["parallelism"], "ddp": res["config"]["ddp"],
+               "allreduce_bytes_per_step": res["config"]["allreduce_bytes_per_step"],
+               "trainable_params": res["config"]["trainable_params"], "host_opt": res["config"]["host_opt"],
+               "host_opt_check": res["config"]["host_opt_check"], "loss": res["loss"], "dtype": "f32",
+               "workload": res["config"]["workload"],
+               "timing": "CUDA events around every step on the training stream, mean over the timed steps, max over ranks"}
+        if res.get("msda"):
+            out["msda_share_of_gpu_time"] = res["msda"]["msda_share_of_gpu_time"]
+            out["msda_kernel_ms_per_step"] = res["msda"]["msda_kernel_ms_per_step"]
+            out["gpu_kernel_ms_per_step"] = res["msda"]["gpu_kernel_ms_per_step"]
+        if res.get("breakdown"):
+            bd = res["breakdown"]
+            out["breakdown"] = {k: v for k, v in bd.items() if k != "criterion_parts_ms"}
+            host_bound = [k for k, v in out["breakdown"].items() if v["host_issue_ms"] > 1.05 * v["gpu_span_ms"] and v["host_issue_ms"] > 1.0]
+            out["limited_by"] = ("host issue time exceeds GPU time in: " + ", ".join(host_bound)) if host_bound else "GPU time in every phase"
+        if world == 1 and not args.no_ref_cuda:
+            cmd = [sys.executable, os.path.join(ROOT, "tools", "train_step_bench.py"), "--op", "ref_cuda", "--steps",
+                   str(max(5, args.train_steps // 2)), "--warmup", str(args.train_warmup)]
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+                ref = json.loads(r.stdout.strip().splitlines()[-1])
+                out["ref_cuda_op"] = {"value": ref["value"], "unit": "img/s", "ms_per_step": ref["ms_per_step"],
+                                      "what": "same model, criterion and optimizer with the reference's own ops/ Python on the "
+                                              "reference's CUDA kernels recompiled for sm_100a (oracle/_ref), host sections as the reference has them"}
+            except Exception as exc:  # noqa: BLE001
+                out["ref_cuda_op"] = {"unavailable": repr(exc)[:200]}
+        return out
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        return {"unavailable": repr(exc)[:300], "trace": traceback.format_exc()[-600:]} if rank == 0 else None
 
 
 def load_traffic(kernel):
@@ -443,6 +501,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--tune", default="", help="A/B only: comma-separated key=value for msda_set_tuning")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the MonoDETR training-step section (configs[3])")
+    ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--train-warmup", type=int, default=6)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     from monosowa_b200 import workloads as W

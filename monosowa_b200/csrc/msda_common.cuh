@@ -50,13 +50,19 @@ struct Tap {
     bool inside;
 };
 
-// cuh:285-288.  The product is rounded before the subtraction (no FMA contraction) so that
-// floor() lands exactly where the reference's scalar_t arithmetic puts it.
+// cuh:285-288: `h_im = loc_h * spatial_h - 0.5`.  What the reference EXECUTES there is one fused multiply-add:
+// nvcc (default -fmad=true) compiles the line to `FFMA h_im, loc_h, (float)spatial_h, -0.5` for scalar_t = float and
+// to a DFMA for double (cuobjdump -sass of oracle/_ref/libmsda_ref_sm100.so, ms_deformable_im2col_gpu_kernel<float>).
+// The single rounding matters exactly where MonoDETR starts training: the module's initial sampling offsets are whole
+// pixels from a pixel centre (ms_deform_attn.py:106-115), so every initial sample sits ON a pixel boundary and
+// floor() of the two-rounding form lands on the other side for ~1e-4 of them -- d out / d loc is discontinuous there
+// (round 1 rounded the product first and disagreed with the reference kernels on 862 of 5.2 M initial gradients;
+// tests/test_msda_gpu.py::test_matches_reference_cuda_kernels now covers that distribution).
 __device__ __forceinline__ Tap<float> make_tap(float loc_x, float loc_y, int H, int W)
 {
     Tap<float> t;
-    const float py = __fmul_rn(loc_y, (float)H) - 0.5f;
-    const float px = __fmul_rn(loc_x, (float)W) - 0.5f;
+    const float py = __fmaf_rn(loc_y, (float)H, -0.5f);
+    const float px = __fmaf_rn(loc_x, (float)W, -0.5f);
     t.inside = (py > -1.f) && (px > -1.f) && (py < (float)H) && (px < (float)W);
     const float fy = floorf(py), fx = floorf(px);
     t.y0 = (int)fy;
@@ -69,8 +75,8 @@ __device__ __forceinline__ Tap<float> make_tap(float loc_x, float loc_y, int H, 
 __device__ __forceinline__ Tap<double> make_tap(double loc_x, double loc_y, int H, int W)
 {
     Tap<double> t;
-    const double py = __dmul_rn(loc_y, (double)H) - 0.5;
-    const double px = __dmul_rn(loc_x, (double)W) - 0.5;
+    const double py = __fma_rn(loc_y, (double)H, -0.5);
+    const double px = __fma_rn(loc_x, (double)W, -0.5);
     t.inside = (py > -1.0) && (px > -1.0) && (py < (double)H) && (px < (double)W);
     const double fy = floor(py), fx = floor(px);
     t.y0 = (int)fy;

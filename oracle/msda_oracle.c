@@ -24,7 +24,9 @@
  *   *_f64 : everything in double (the parity yardstick).
  *   *_f32 : the same loops in float, compiled with -ffp-contract=off, so that floor()
  *           decisions follow fp32 arithmetic exactly as the reference kernel's
- *           scalar_t=float instantiation does (loc*H rounded to float, then -0.5).
+ *           scalar_t=float instantiation does: the pixel coordinate is ONE fused
+ *           multiply-add, fma(loc, H, -0.5) -- what nvcc makes of cuh:285-286 (FFMA / DFMA
+ *           in the SASS of the compiled reference); everything else is not contracted.
  *
  * Build: see oracle/Makefile (gcc -O2 -fopenmp -ffp-contract=off -shared -fPIC).
  */
@@ -33,6 +35,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#define ORACLE_FMA_f64(a, b, c) fma((a), (b), (c))
+#define ORACLE_FMA_f32(a, b, c) fmaf((a), (b), (c))
+
 #define DEFINE_ORACLE(SUFFIX, real)                                                          \
                                                                                              \
 /* one bilinear tap set; returns 1 when the sample is inside the (-1,H)x(-1,W) window */     \
@@ -40,10 +45,8 @@ static int tap_##SUFFIX(real loc_x, real loc_y, int H, int W,                   
                         int *y0, int *x0, real *ly, real *lx)                                \
 {                                                                                            \
     /* cuh:285-286 : pixel coordinate, align_corners=False convention */                     \
-    real ty = loc_y * (real)H;                                                               \
-    real tx = loc_x * (real)W;                                                               \
-    real py = ty - (real)0.5;                                                                \
-    real px = tx - (real)0.5;                                                                \
+    real py = ORACLE_FMA_##SUFFIX(loc_y, (real)H, (real)-0.5);                               \
+    real px = ORACLE_FMA_##SUFFIX(loc_x, (real)W, (real)-0.5);                               \
     /* cuh:288 */                                                                            \
     if (!(py > (real)-1 && px > (real)-1 && py < (real)H && px < (real)W)) return 0;         \
     real fy = floor(py), fx = floor(px);                                                     \

@@ -563,9 +563,13 @@ def test_beyond_int32_indexing(msda, cuda_device):
 # --------------------------------------------------------------------------------------------
 @pytest.mark.skipif(not O.ref_cuda_available(), reason="oracle/_ref not built (needs /root/reference at build time)")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-def test_matches_reference_cuda_kernels(msda, cuda_device, dtype):
+@pytest.mark.parametrize("loc_mode", ["model", "init"])
+def test_matches_reference_cuda_kernels(msda, cuda_device, dtype, loc_mode):
+    """`init`: the module's initial offsets (whole pixels from a pixel centre, ms_deform_attn.py:106-115) put EVERY
+    sample on a pixel boundary, where d out / d loc jumps: only the reference's exact coordinate arithmetic -- one
+    fused multiply-add, see make_tap in msda_common.cuh -- reproduces its floor() decisions."""
     from monosowa_b200 import workloads as W
-    wl = W.config(0, batch=2, dtype=dtype)
+    wl = W.config(0, batch=2, dtype=dtype, loc_mode=loc_mode)
     d = W.make_inputs(wl, device=cuda_device)
     ours = torch.ops.msda.forward(d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"], 64)
     ref = O.ref_cuda_forward(d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"])

@@ -106,7 +106,7 @@ def prepare_targets(targets, batch_size):                 # trainer_helper.py:18
     return [{k: targets[k][i][mask[i]] for k in keys} for i in range(batch_size)]
 
 
-def main():
+def make_parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=8)
@@ -126,16 +126,33 @@ def main():
                     help="infer: model.eval() forward only (50 queries), as tester_helper.py:80-99")
     ap.add_argument("--amp", default="none", choices=["none", "bf16"],
                     help="bf16: autocast around the model forward (beyond the reference, which trains in fp32)")
-    args = ap.parse_args()
+    ap.add_argument("--no-fuse", action="store_true", help="parity mode: MSDeformAttn.fuse_preprocessing = False (literal path)")
+    ap.add_argument("--dump-step", default="",
+                    help="parity mode (tests/test_train_step_gpu.py): run ONE deterministic training step (seeded, dropout "
+                         "off, no optimizer step) and save the loss terms and a sample of parameter gradients to this file")
+    return ap
 
+
+def default_args(**over):
+    """argparse defaults as a namespace (bench.py calls run() without a command line)"""
+    args = make_parser().parse_args([])
+    for k, v in over.items():
+        setattr(args, k, v)
+    return args
+
+
+def run(args):
+    """One measurement; returns the result dict on rank 0 (None elsewhere).  Uses the default process group if one is
+    initialised (bench.py under torchrun) and creates it otherwise when WORLD_SIZE > 1."""
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    own_pg = False
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
+            own_pg = True
     os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 8) // max(world, 1))))
     torch.set_num_threads(max(1, (os.cpu_count() or 8) // max(world, 1)))
 
@@ -169,6 +186,29 @@ def main():
         del out0
     img_sizes = tdict["img_size"]
     weight_dict = criterion.weight_dict
+
+    if args.dump_step:
+        # One deterministic step for the ours-vs-reference-kernels parity test: dropout off (the two op
+        # implementations must see the same network), fixed seed, gradients of a fixed sample of parameters.
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+            if args.no_fuse and hasattr(mod, "fuse_preprocessing"):
+                mod.fuse_preprocessing = False
+        torch.manual_seed(1234)
+        optimizer.zero_grad()
+        outputs = model(images, calibs, targets, img_sizes, dn_args=None)
+        ld = criterion(outputs, targets, None, None)
+        loss = sum(ld[k] * weight_dict[k] for k in ld.keys() if k in weight_dict)
+        loss.backward()
+        torch.cuda.synchronize()
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and p.grad is not None]
+        pick = [named[i] for i in range(0, len(named), max(1, len(named) // 48))]
+        torch.save({"loss": float(loss), "loss_terms": {k: float(v) for k, v in ld.items()},
+                    "grads": {n: p.grad.detach().float().cpu() for n, p in pick},
+                    "grad_norm_all": float(torch.sqrt(sum(p.grad.double().pow(2).sum() for _, p in named))),
+                    "op": args.op, "host_opt": host_opt, "n_params_with_grad": len(named)}, args.dump_step)
+        return {"dumped": args.dump_step, "loss": float(loss), "op": args.op}
 
     net = model
     if world > 1:
@@ -323,19 +363,31 @@ def main():
         for i in range(3):
             step(i + 1)                                          # keep the ranks in lock step
 
+    result = None
     if rank == 0:
         med, mean, wallms = ms.tolist()
-        print(json.dumps({
+        result = {
             "metric": "MonoDETR train img/s" if args.mode == "train" else "MonoDETR inference img/s", "value": args.batch * world / (mean * 1e-3), "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean, "ms_per_step_median": med,
             "ms_per_step_wall": wallms, "scaling": "weak", "higher_is_better": True, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE.json configs[3]: unmodified reference MonoDETR (ResNet-50, 3 enc + 3 dec layers) + "
                                    "SetCriterion + reference AdamW, synthetic KITTI batch", "batch_per_gpu": args.batch,
                        "global_batch": args.batch * world, "image": [384, 1280], "msda_op": args.op, "host_opt": host_opt, "host_opt_check": host_opt_check, "logging": args.logging, "mode": args.mode, "amp": args.amp,
-                       "parallelism": f"ddp{world}", "ddp": args.ddp, "trainable_params": n_params},
-            "loss": float(loss), "msda": share, "breakdown": breakdown}), flush=True)
-    if world > 1:
+                       "parallelism": f"ddp{world}", "ddp": args.ddp, "trainable_params": n_params,
+                       "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0},
+            "loss": float(loss), "msda": share, "breakdown": breakdown}
+    del net, model, criterion, optimizer
+    torch.cuda.empty_cache()
+    if own_pg:
         dist.destroy_process_group()
+    return result
+
+
+def main():
+    args = make_parser().parse_args()
+    result = run(args)
+    if result is not None:
+        print(json.dumps(result), flush=True)
 
 
 if __name__ == "__main__":
