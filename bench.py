@@ -114,20 +114,62 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU implementation (oracle port of ms_deform_attn_core_pytorch)
+# reference arm: the reference's own CPU implementation of the path (ms_deform_attn_core_pytorch)
 # ------------------------------------------------------------------------------------------
-def cpu_reference_step_fn(wl, sample_batch):
-    """Returns (step, bytes_per_step, description).  The sample is `sample_batch` images of the
-    workload -- the grid_sample path materialises (N*M, D, Lq, L*P) and needs ~0.7 s/image-pair."""
-    from oracle import msda_oracle as O                      # checker used as the CPU baseline only
-    from monosowa_b200 import workloads as W
+def load_workloads():
+    """monosowa_b200/workloads.py as a stand-alone module: pure tensor plumbing, and importing it this way does NOT
+    import the package, i.e. does not load libmsda_b200.so -- the reference arm must not touch the product."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_msda_workloads", os.path.join(ROOT, "monosowa_b200", "workloads.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_msda_workloads"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+REF_FUNC_FILE = os.path.join(ROOT, "baseline", "_ref", "MonoDETR", "lib", "models", "monodetr", "ops", "functions",
+                             "ms_deform_attn_func.py")
+
+
+def load_reference_core():
+    """The UNMODIFIED reference function ms_deform_attn_core_pytorch (ops/functions/ms_deform_attn_func.py:41-61) from
+    the staged reference tree (baseline/_ref, tools/stage_reference.py).  The file imports the compiled extension at
+    line 18; an empty stand-in module satisfies that import (the function itself never touches it).  None if the tree
+    is not staged."""
+    if not os.path.exists(REF_FUNC_FILE):
+        return None
+    import importlib.util
+    import types
+    sys.modules.setdefault("MultiScaleDeformableAttention", types.ModuleType("MultiScaleDeformableAttention"))
+    spec = importlib.util.spec_from_file_location("_ref_ms_deform_attn_func", REF_FUNC_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.ms_deform_attn_core_pytorch
+
+
+def cpu_reference_step_fn(wl, sample_batch, W=None):
+    """Returns (step, bytes_per_step, description, kind).  The sample is `sample_batch` images of the
+    workload -- the grid_sample path materialises (N*M, D, Lq, L*P) and needs ~0.1 s per image."""
+    W = W or load_workloads()
     swl = W.config(1, batch=sample_batch, loc_mode=wl.loc_mode, seed=wl.seed)
     d = W.make_inputs(swl, device="cpu")
+    core = load_reference_core()
+    kind = "reference"
+    what = "the reference's own ms_deform_attn_core_pytorch (baseline/_ref, unmodified) forward + autograd backward"
+    if core is None:                                         # tree not staged: the oracle's restatement of the same function
+        from oracle import msda_oracle as O                  # checker used as the CPU baseline only
+        core, kind = O.core_grid_sample, "port"
+        what = "oracle.core_grid_sample (restated ms_deform_attn_core_pytorch, grid_sample) forward + autograd backward"
 
     def step():
-        O.core_grid_sample_fwd_bwd(d["value"], d["shapes"], d["loc"], d["attn"], d["grad_out"])
+        v = d["value"].detach().clone().requires_grad_(True)
+        l = d["loc"].detach().clone().requires_grad_(True)
+        a = d["attn"].detach().clone().requires_grad_(True)
+        out = core(v, d["shapes"], l, a)
+        out.backward(d["grad_out"].reshape(out.shape))
+        return out
 
-    return step, W.algorithmic_bytes(swl)["total"], f"{sample_batch} of {wl.batch} images of {wl.name} per step"
+    return step, W.algorithmic_bytes(swl)["total"], f"{sample_batch} of {wl.batch} images of {wl.name} per step", kind, what
 
 
 def time_cpu(step, steps, warmup):
@@ -147,7 +189,7 @@ def run_reference_arm(args, wl):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step, nbytes, sample = cpu_reference_step_fn(wl, sample_batch=2)
+    step, nbytes, sample, kind, what = cpu_reference_step_fn(wl, sample_batch=2)
     steps = max(1, min(args.steps, 8))
     ms = time_cpu(step, steps, max(1, min(args.warmup, 2)))
     val = nbytes / (ms * 1e-3) / 1e9
@@ -156,8 +198,9 @@ def run_reference_arm(args, wl):
         "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(wl, world),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
-                         "what": "oracle.core_grid_sample (restated ms_deform_attn_core_pytorch, grid_sample) fwd + autograd bwd"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
+                         "what": what},
+        "native_libraries_loaded": [m for m in ("monosowa_b200", "monosowa_b200._lib") if m in sys.modules],
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -251,6 +294,20 @@ def run_ours(args, wl):
 
     value, ms_max = aggregate(ab["total"], ms_step, world, reduce_fn if use_dist else None)
 
+    # sustained figure: the timed region above lasts tens of milliseconds at the driver's K; this block runs
+    # `--sustain-steps` more steps back to back (one event pair, >= 0.2 s) so that a power-capped clock shows
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.sustain_steps):
+        keep = step_device()
+    s1.record()
+    barrier()
+    del keep
+    value_sustained, ms_sustained = aggregate(ab["total"], s0.elapsed_time(s1) / max(args.sustain_steps, 1), world,
+                                              reduce_fn if use_dist else None)
+    live_rows = W.live_corner_rows(d, wl)                    # gathered (and scattered) 128-byte rows that carry weight
+
     # ---- end to end: pinned host buffers in, results back to pinned host buffers -------------
     # Device staging buffers and pinned result buffers are allocated once; every step copies all
     # inputs host->device and all four results device->host, chunked over the batch on three
@@ -338,16 +395,27 @@ def run_ours(args, wl):
             torch.cuda.synchronize()
             best = min(best, time.perf_counter() - t0)
         return best
-    pcie = None
-    if world == 1:
-        t_h, t_d, t_b = copy_rate(True, False), copy_rate(False, True), copy_rate(True, True)
-        pcie = {"h2d_GBps": h2d_bytes / t_h / 1e9, "d2h_GBps": d2h_bytes / t_d / 1e9,
-                "duplex_ms": t_b * 1e3, "note": "full-duplex copy of one step's inputs and results, no kernels: "
-                                                "the floor of an e2e step on this box"}
+    # all ranks copy at the same time (barrier in front of every probe), slowest rank counts: at N > 1 this is what the
+    # box's host memory / PCIe fabric gives N GPUs together, i.e. the floor the N-GPU e2e figure has to be read against
+    def probe(h2d, d2h):
+        barrier()
+        t = torch.tensor([copy_rate(h2d, d2h)], dtype=torch.float64)
+        return float((reduce_fn(t, "max") if use_dist else t).item())
+    t_h, t_d, t_b = probe(True, False), probe(False, True), probe(True, True)
+    pcie = {"h2d_GBps": h2d_bytes * world / t_h / 1e9, "d2h_GBps": d2h_bytes * world / t_d / 1e9,
+            "duplex_ms": t_b * 1e3, "ranks_copying_at_once": world,
+            "note": "full-duplex copy of one step's inputs and results on every rank at once, no kernels: the floor of an "
+                    "e2e step on this box (whole-job GB/s per direction; duplex_ms = slowest rank)"}
     e2e_value, e2e_ms_max = aggregate(ab["total"], e2e_ms, world, reduce_fn if use_dist else None)
     chk = chk and (torch.equal(host_out[0].to(dev), out) if rank == 0 else True)   # both e2e paths reproduce the device forward
 
     ref_cuda = time_reference_cuda(d, ab, args) if (world == 1 and rank == 0 and not args.no_ref_cuda) else None
+    other = None
+    if world == 1 and not args.no_other_configs:
+        try:
+            other = other_configs_table(msda, W, dev)
+        except Exception as exc:  # noqa: BLE001
+            other = [{"unavailable": repr(exc)[:200]}]
 
     # ---- the second half of BASELINE.json's metric: the MonoDETR training step (configs[3]) on the same ranks ------
     kernels = {"fwd": msda._lib.describe("forward", wl.dtype, wl.batch, wl.heads, wl.head_dim, wl.L, wl.points, wl.Lq),
@@ -367,11 +435,13 @@ def run_ours(args, wl):
     peak, peak_src = measured_peak()
     dom = ("bwd", bwd_ms, ab["bwd"]) if bwd_ms >= fwd_ms else ("fwd", fwd_ms, ab["fwd"])
     achieved = dom[2] / (dom[1] * 1e-3) / 1e9
+    ceiling = binding_ceiling(live_rows, load_traffic("bwd_red_lines_per_image"), wl.batch)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {torch.float32: "f32", torch.bfloat16: "bf16", torch.float64: "f64"}[wl.dtype], "data": "synthetic",
         "config": workload_config(wl, world),
+        "value_sustained": value_sustained, "ms_per_step_sustained": ms_sustained, "sustain_steps": args.sustain_steps,
         "frac_of_hbm_peak": value / world / peak,
         "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
         "fwd_GBps": ab["fwd"] / (fwd_ms * 1e-3) / 1e9, "bwd_GBps": ab["bwd"] / (bwd_ms * 1e-3) / 1e9,
@@ -380,9 +450,14 @@ def run_ours(args, wl):
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": load_traffic(dom[0]), "peak_source": peak_src,
                      "note": "achieved = algorithmic bytes of the launch / CUDA-event time on the launch stream; "
-                             "bwd includes its cudaMemsetAsync of grad_value"},
+                             "bwd includes its cudaMemsetAsync of grad_value",
+                     # the HBM roofline is not the binding one for this gather/scatter:
+                     "binding_unit": ceiling["binding_unit"], "binding_ceiling": ceiling,
+                     "frac_of_binding_ceiling": ceiling["fwd_plus_bwd_floor_ms"] / (fwd_ms + bwd_ms),
+                     "frac_of_binding_ceiling_dominant_kernel": ceiling[dom[0] + "_floor_ms"] / dom[1]},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_max, "h2d_bytes_per_step": h2d_bytes * world,
                 "d2h_bytes_per_step": d2h_bytes * world, "bytes_note": "whole job (all ranks), like `value`", "chunks": chunks, "matches_device_path": out_shape_checked, "pcie": pcie,
+                "frac_of_pcie_floor": (pcie["duplex_ms"] / e2e_ms_max) if pcie else None,
                 "api": "msda_host_step_f32 (C ABI, pinned host buffers in and out; monosowa_b200.host_step), "
                        f"{args.e2e_images_per_chunk} image(s) per pipeline chunk",
                 "autograd_api_ms_per_step": e2e_autograd_ms,
@@ -391,14 +466,15 @@ def run_ours(args, wl):
         "clocks": clocks,
         "lib": msda._lib.build_info(),
         "train_step": train,
+        "other_configs": other,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        step, nbytes, sample = cpu_reference_step_fn(wl, sample_batch=2)
+        step, nbytes, sample, kind, what = cpu_reference_step_fn(wl, sample_batch=2, W=W)
         ms = time_cpu(step, args.cpu_steps, 1)
         line["cpu_baseline"] = {"value": nbytes / (ms * 1e-3) / 1e9, "unit": UNIT, "cores": torch.get_num_threads(),
-                                "kind": "port", "sample": sample + f", {args.cpu_steps} timed steps", "ms_per_step": ms}
+                                "kind": kind, "what": what, "sample": sample + f", {args.cpu_steps} timed steps", "ms_per_step": ms}
     if ref_cuda is not None:
         line["ref_cuda_kernel"] = ref_cuda
     print(json.dumps(line), flush=True)
@@ -435,8 +511,14 @@ def train_step_section(args, rank, world):
         if res.get("breakdown"):
             bd = res["breakdown"]
             out["breakdown"] = {k: v for k, v in bd.items() if k != "criterion_parts_ms"}
-            host_bound = [k for k, v in out["breakdown"].items() if v["host_issue_ms"] > 1.05 * v["gpu_span_ms"] and v["host_issue_ms"] > 1.0]
-            out["limited_by"] = ("host issue time exceeds GPU time in: " + ", ".join(host_bound)) if host_bound else "GPU time in every phase"
+            # a phase whose host issue time equals its GPU span is paced by the host: the GPU finishes each kernel before
+            # the next one is launched, so the span cannot be shorter than the time Python needs to issue the phase
+            host_bound = [k for k, v in out["breakdown"].items() if v["host_issue_ms"] >= 0.95 * v["gpu_span_ms"] and v["host_issue_ms"] > 1.0]
+            gpu_bound = [k for k, v in out["breakdown"].items() if v["host_issue_ms"] < 0.95 * v["gpu_span_ms"] and v["gpu_span_ms"] > 1.0]
+            out["limited_by"] = {"host_issue_bound_phases": host_bound, "gpu_bound_phases": gpu_bound,
+                                 "note": "host-bound phases run the reference's Python at its own pace (ResNet-50 with Python "
+                                         "FrozenBatchNorm, ~2000 small launches per forward); they are identical on every rank, "
+                                         "which is why the step scales: DDP's 149.8 MB all-reduce overlaps the GPU-bound backward"}
         if world == 1 and not args.no_ref_cuda:
             cmd = [sys.executable, os.path.join(ROOT, "tools", "train_step_bench.py"), "--op", "ref_cuda", "--steps",
                    str(max(5, args.train_steps // 2)), "--warmup", str(args.train_warmup)]
@@ -452,6 +534,68 @@ def train_step_section(args, rank, world):
     except Exception as exc:  # noqa: BLE001
         import traceback
         return {"unavailable": repr(exc)[:300], "trace": traceback.format_exc()[-600:]} if rank == 0 else None
+
+
+# Measured unit rates behind the binding ceiling (B200, this pool; microbenchmarks under tools/ubench, outputs under
+# profiles/): rows = 128-byte (pixel, head) rows of `value` / `grad_value`
+L2_TO_SM_ROWS_PER_S = 20.6e12 / 128          # L2-resident random row gather, all SMs (r01_ubench_gather_rows.txt: 20.6 TB/s)
+L1_PIPE_ROWS_PER_S = 148 * 1.965e9           # one row per clock per SM through the L1 data pipe (LDS.128 rows: 1.06 clk)
+L2_RED_LINES_PER_S = 49.6e9                  # REDG.128 lines absorbed by L2 chip-wide (r01b_ubench_lines_per_instruction.txt)
+
+
+def binding_ceiling(live_rows, red_lines_per_image, batch):
+    """Attainable floor of forward and backward from the units that actually bind them:
+    forward  = live corner rows / L2->SM row-fill rate (the rows do not fit L1; 0.245 ms more if they all did);
+    backward = max(the same gather, the reduction lines its scatter sends to L2 / L2's reduction rate)."""
+    red_lines = (red_lines_per_image or 0) * batch
+    fwd = live_rows / L2_TO_SM_ROWS_PER_S * 1e3
+    bwd_gather = live_rows / L2_TO_SM_ROWS_PER_S * 1e3
+    bwd_red = red_lines / L2_RED_LINES_PER_S * 1e3
+    return {"binding_unit": "forward: L2->SM row fills / L1 data pipe (one 128-byte row per sample corner); backward: "
+                            "L2 reduction rate (REDG.128 lines) and the same gather",
+            "live_rows_per_launch": live_rows, "bwd_reduction_lines_per_launch": red_lines,
+            "rates": {"l2_to_sm_rows_per_s": L2_TO_SM_ROWS_PER_S, "l1_pipe_rows_per_s": L1_PIPE_ROWS_PER_S,
+                      "l2_reduction_lines_per_s": L2_RED_LINES_PER_S},
+            "fwd_floor_ms": fwd, "fwd_floor_if_all_rows_hit_l1_ms": live_rows / L1_PIPE_ROWS_PER_S * 1e3,
+            "bwd_floor_ms": max(bwd_gather, bwd_red), "fwd_plus_bwd_floor_ms": fwd + max(bwd_gather, bwd_red),
+            "source": "unit rates: tools/ubench microbenchmarks (profiles/r01_ubench_gather_rows.txt, "
+                      "r01b_ubench_lines_per_instruction.txt); reduction lines: ncu lts__t_requests_srcunit_tex_op_red of the "
+                      "shipped backward at configs[1] (profiles/traffic.json); live rows counted from this run's locations"}
+
+
+def other_configs_table(msda, W, dev, iters=10):
+    """BASELINE.json configs[2] (decoder, bf16, 50 / 550 queries, batch 16) and configs[4] (large-image shapes, batch 4,
+    fp32 + bf16) timed on this GPU with the same kernels: parity-tested elsewhere, reported here so that the driver's
+    record has them (N = 1 only; no roofline claim: these shapes are launch-latency or small-grid bound)."""
+    rows = []
+    wls = [W.config(2, num_queries=50), W.config(2, num_queries=550)] + W.sweep_config5(batch=4)
+    for wl in wls:
+        d = W.make_inputs(wl, device=dev)
+        ab = W.algorithmic_bytes(wl)
+        a5 = (d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"])
+
+        def timeit(fn):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+
+        f = timeit(lambda: torch.ops.msda.forward(*a5, 64))
+        b = timeit(lambda: torch.ops.msda.backward(*a5, d["grad_out"], 64))
+        rows.append({"workload": wl.name, "dtype": str(wl.dtype).replace("torch.", ""), "batch": wl.batch, "S": wl.S,
+                     "queries": wl.Lq, "fwd_us": round(f * 1e3, 1), "bwd_us": round(b * 1e3, 1),
+                     "GBps": round(ab["total"] / (f + b) / 1e6, 1),
+                     "kernels": [msda._lib.describe("forward", wl.dtype, wl.batch, wl.heads, wl.head_dim, wl.L, wl.points, wl.Lq),
+                                 msda._lib.describe("backward", wl.dtype, wl.batch, wl.heads, wl.head_dim, wl.L, wl.points, wl.Lq)]})
+        del d, a5
+        torch.cuda.empty_cache()
+    return rows
 
 
 def load_traffic(kernel):
@@ -502,16 +646,18 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--tune", default="", help="A/B only: comma-separated key=value for msda_set_tuning")
     ap.add_argument("--no-train-step", action="store_true", help="skip the MonoDETR training-step section (configs[3])")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the configs[2] / configs[4] timing table")
+    ap.add_argument("--sustain-steps", type=int, default=100)
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--train-warmup", type=int, default=6)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    from monosowa_b200 import workloads as W
-    wl = W.config(1, batch=args.batch, loc_mode=args.loc_mode)
     if args.impl == "reference":
-        run_reference_arm(args, wl)
+        W = load_workloads()                        # never imports the package: the product library stays unloaded
+        run_reference_arm(args, W.config(1, batch=args.batch, loc_mode=args.loc_mode))
     else:
-        run_ours(args, wl)
+        from monosowa_b200 import workloads as W
+        run_ours(args, W.config(1, batch=args.batch, loc_mode=args.loc_mode))
 
 
 if __name__ == "__main__":

@@ -93,8 +93,12 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     for (int b0 = 0; b0 < LP; b0 += G) {
         const int sidx = b0 + gl;
         const bool has = w.valid && sidx < LP;
-        const SampleGeom gm = build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, has && d.S > 0, in, s_lv,
-                                           sidx / d.P, xs);
+        int4 roff;
+        float4 rwa;
+        const SampleGeom gm = sample_geometry(has && d.S > 0, in, s_lv, sidx / d.P, xs, roff, rwa);
+        if (!gm.live) roff.x = -1;                               // consumers skip the gathers of this sample
+        *reinterpret_cast<int4 *>(grp + gl * 4) = roff;
+        *reinterpret_cast<float4 *>(grp + RL::WEIGHTS + gl * 4) = rwa;
         const float a_cur = in.a, ex_cur = in.ex, ey_cur = in.ey;
         __syncwarp();
         in = fetch(sidx + G);                                                              // next batch, in flight
@@ -114,7 +118,9 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 t[4 * u] = t[4 * u + 1] = t[4 * u + 2] = t[4 * u + 3] = 0.f;
                 const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
                 const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
-                if (d.S > 0) {
+                // a sample outside the window (or past L*P) reads nothing, like the reference's branch (cuh:288, 365-367):
+                // its lanes are predicated off, so it costs no L1 wavefronts (15 % of the samples at MonoDETR's shapes)
+                if (off.x >= 0) {
                     float v00[4], v01[4], v10[4], v11[4];
                     Vec4<VT>::template gather<LOADH>(vimg + off.x, v00);
                     Vec4<VT>::template gather<LOADH>(vimg + off.y, v01);
@@ -377,9 +383,9 @@ int backward_any(DType dt, const void *value, const int64_t *shapes, const int64
     int rc = kUnsupported;
     if ((long)d.N * d.Lq * d.M == 0) {
         rc = 0;
-    } else if (tiled_backward_applies(d, dt, vec_ok)) {
+    } else if (!direct_bf16 && tiled_backward_applies(d, dt, vec_ok)) {
         rc = launch_backward_tiled(dt, value, shapes, lsi, loc, attn, grad_out, acc, gl, ga, d, ref, ref_dim, st);
-    } else if (binned_backward_applies(d, dt, vec_ok)) {
+    } else if (!direct_bf16 && binned_backward_applies(d, dt, vec_ok)) {
         rc = launch_backward_binned(dt, value, shapes, lsi, loc, attn, grad_out, acc, gl, ga, d, ref, ref_dim, st);
     } else if (dt != DType::F64 && use_rec(d, vec_ok)) {
 #define ARGS value, shapes, lsi, loc, attn, grad_out, acc, gl, ga, d, ref, ref_dim, st
@@ -413,9 +419,11 @@ int backward_any(DType dt, const void *value, const int64_t *shapes, const int64
 bool backward_needs_scratch(const Dims &d, DType dt, bool vec_ok)
 {
     if (dt != DType::BF16) return false;
-    if (tiled_backward_applies(d, dt, vec_ok) || binned_backward_applies(d, dt, vec_ok) || !use_rec(d, vec_ok)) return true;
+    if (!use_rec(d, vec_ok)) return true;
+    if (tuning().bf16_direct < 0 && (tiled_backward_applies(d, dt, vec_ok) || binned_backward_applies(d, dt, vec_ok))) return true;
     if (grid_for(d, 1, 32 / max(1, d.D / kChannelsPerLane), 256) > 0x7fffffffL) return true;
-    return (long)d.Lq * d.L * d.P * 4 > 4L * d.S;
+    const long max_adds = tuning().bf16_direct >= 0 ? tuning().bf16_direct : 4;
+    return (long)d.Lq * d.L * d.P * 4 > max_adds * d.S;
 }
 
 int launch_backward_fused(DType dt, const void *value, const int64_t *shapes, const int64_t *lsi, const void *ref,

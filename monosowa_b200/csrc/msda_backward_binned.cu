@@ -168,7 +168,12 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
             const int sidx = b0 + gl;
             const bool has = qvalid && sidx < LP;
             const int l = sidx / d.P;
-            const SampleGeom gm = build_record(grp + gl * 4, grp + RL::WEIGHTS + gl * 4, has && d.S > 0, in, s_lv, l, xs);
+            int4 roff;
+            float4 rwa;
+            const SampleGeom gm = sample_geometry(has && d.S > 0, in, s_lv, l, xs, roff, rwa);
+            if (!gm.live) roff.x = -1;                           // consumers skip the gathers of this sample
+            *reinterpret_cast<int4 *>(grp + gl * 4) = roff;
+            *reinterpret_cast<float4 *>(grp + RL::WEIGHTS + gl * 4) = rwa;
             const float a_cur = in.a, ex_cur = in.ex, ey_cur = in.ey;
             if (has && sidx >= lbP) {
                 // binned level: park the sample instead of sending its four reduction lines to L2
@@ -205,7 +210,12 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                         const int s = h * GH + u0 + j;
                         off[j] = *reinterpret_cast<const int4 *>(grp + s * 4);
                         wa[j] = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
-                        if (d.S > 0) {
+                        v[j][0][0] = v[j][0][1] = v[j][0][2] = v[j][0][3] = 0.f;
+                        v[j][1][0] = v[j][1][1] = v[j][1][2] = v[j][1][3] = 0.f;
+                        v[j][2][0] = v[j][2][1] = v[j][2][2] = v[j][2][3] = 0.f;
+                        v[j][3][0] = v[j][3][1] = v[j][3][2] = v[j][3][3] = 0.f;
+                        // outside the window / past L*P: nothing is read (the reference's branch, cuh:288, 365-367)
+                        if (off[j].x >= 0) {
                             Vec4<VT>::template gather<LOADH>(vimg + off[j].x, v[j][0]);
                             Vec4<VT>::template gather<LOADH>(vimg + off[j].y, v[j][1]);
                             Vec4<VT>::template gather<LOADH>(vimg + off[j].z, v[j][2]);

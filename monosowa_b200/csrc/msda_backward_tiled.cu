@@ -237,6 +237,7 @@ bwd_tile_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
                         }
                         s_ent[ql * G + gl] = e;
                     }
+                    if (!gm.live) off.x = -1;                    // consumers skip the gathers of this sample
                     *reinterpret_cast<int4 *>(grp + gl * 4) = off;
                     *reinterpret_cast<float4 *>(grp + RL::WEIGHTS + gl * 4) = wa;
                     const unsigned smask = __ballot_sync(kFullMask, stray) >> (k * G);   // bit s: sample s of MY group is a stray
@@ -261,7 +262,7 @@ bwd_tile_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
                             const int s = h * GH + u;
                             t[4 * u] = t[4 * u + 1] = t[4 * u + 2] = t[4 * u + 3] = 0.f;
                             const int4 o4 = *reinterpret_cast<const int4 *>(grp + s * 4);
-                            if (d.S > 0) {
+                            if (o4.x >= 0) {
                                 float v00[4], v01[4], v10[4], v11[4];
                                 Vec4<VT>::template gather<0>(vimg + o4.x, v00);
                                 Vec4<VT>::template gather<0>(vimg + o4.y, v01);

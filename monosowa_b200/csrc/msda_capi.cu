@@ -421,6 +421,7 @@ static int *tuning_slot(const char *key)
     if (!strcmp(key, "bwd_variant")) return &tuning().bwd_variant;
     if (!strcmp(key, "fwd_pipe")) return &tuning().fwd_pipe;
     if (!strcmp(key, "bwd_pipe")) return &tuning().bwd_pipe;
+    if (!strcmp(key, "bf16_direct")) return &tuning().bf16_direct;
     return nullptr;
 }
 

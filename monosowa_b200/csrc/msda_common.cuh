@@ -200,6 +200,8 @@ struct Tuning {
     int bwd_variant = -1;   // 11 record kernel always, 20 tile kernel always, 21 binned kernel always, 99 generic
     int fwd_pipe = -1;      // launch flavours, -DMSDA_AB builds only
     int bwd_pipe = -1;
+    int bf16_direct = -1;   // bf16 backward: largest average number of additions per grad_value row that may go
+                            // straight into the bf16 gradient (default 4; see backward_needs_scratch)
 };
 Tuning &tuning();
 void count_launch(int n = 1);

@@ -140,6 +140,22 @@ def make_inputs(wl: Workload, device="cpu", seed=None, requires_grad=False):
     return dict(value=value, shapes=sh, lsi=lsi, loc=loc, attn=attn, grad_out=grad_out)
 
 
+def live_corner_rows(d, wl: Workload) -> int:
+    """Number of (sample, corner) rows that carry weight: samples inside the (-1,H)x(-1,W) window (reference
+    ms_deform_im2col_cuda.cuh:288) times their corners inside the map -- the rows a forward has to gather."""
+    loc = d["loc"].float()
+    total = 0
+    for l, (h, w) in enumerate(wl.shapes):
+        px = loc[:, :, :, l, :, 0] * w - 0.5
+        py = loc[:, :, :, l, :, 1] * h - 0.5
+        inside = (px > -1) & (py > -1) & (px < w) & (py < h)
+        x0, y0 = px.floor(), py.floor()
+        nx = ((x0 >= 0) & inside).long() + ((x0 + 1 <= w - 1) & inside).long()
+        ny = ((y0 >= 0) & inside).long() + ((y0 + 1 <= h - 1) & inside).long()
+        total += int((nx * ny).sum().item())
+    return total
+
+
 def algorithmic_bytes(wl: Workload):
     """Compulsory traffic of one forward / one backward: every input read once,
     every output written once; a sparsely gathered tensor counts min(dense, gathered)."""
