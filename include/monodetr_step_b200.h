@@ -47,6 +47,14 @@ enum {
 int detr_group_lsa_f32(const float *cost, const int *sizes, int B, int Q, int T, int groups,
                        int64_t *out_query, int64_t *out_target, void *stream);
 
+/* Same, plus a DEVICE int `status` (may be NULL): bit 0 is OR-ed in when a sub-problem met only non-finite
+ * reduced costs (NaN / Inf in `cost`) and fell back to an arbitrary free column.  scipy raises ValueError
+ * ("matrix contains invalid numeric entries") there, which stops a diverged run; the caller of this library
+ * reads `status` when it next synchronises and raises the same error (monosowa_b200/step_host/lsa.py does, one
+ * matcher call late, without adding a synchronisation to the step). */
+int detr_group_lsa_status_f32(const float *cost, const int *sizes, int B, int Q, int T, int groups,
+                              int64_t *out_query, int64_t *out_target, int *status, void *stream);
+
 const char *detr_step_last_error(void);
 
 #ifdef __cplusplus

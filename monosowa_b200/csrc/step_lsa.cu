@@ -39,7 +39,8 @@ constexpr unsigned kFull = 0xffffffffu;
 // rows i in [1, n], columns j in [1, m]; `rows_are_targets` tells how (i, j) maps onto (query, target)
 __global__ void __launch_bounds__(32)
 group_lsa_kernel(const float *__restrict__ cost, const ImageTable tab, const int Q, const int T, const int groups,
-                 const int nmax, const int mmax, int64_t *__restrict__ out_query, int64_t *__restrict__ out_target)
+                 const int nmax, const int mmax, int64_t *__restrict__ out_query, int64_t *__restrict__ out_target,
+                 int *__restrict__ status)
 {
     extern __shared__ double sm[];
     double *u = sm;                                  // [nmax + 1] row potentials
@@ -90,11 +91,17 @@ group_lsa_kernel(const float *__restrict__ cost, const ImageTable tab, const int
                 const int oj = __shfl_xor_sync(kFull, j1, off);
                 if (od < delta || (od == delta && oj < j1)) { delta = od; j1 = oj; }
             }
-            if (j1 == 0x7fffffff) {                   // only non-finite costs left: take any free column
+            // the scan above wrote minv[] / way[] from lane (j - 1) % 32; the loops below touch minv[j] from lane
+            // j % 32: shuffles order nothing in memory, so the warp is fenced here (independent thread scheduling)
+            __syncwarp();
+            if (j1 == 0x7fffffff) {                   // only non-finite costs left: take any free column ...
                 for (int j = 1; j <= m; ++j)
                     if (!used[j]) { j1 = j; break; }
                 delta = 0.0;
-                if (lane == 0) way[j1] = j0;
+                if (lane == 0) {
+                    way[j1] = j0;
+                    if (status) atomicOr(status, 1);  // ... and say so: scipy raises ValueError on NaN / Inf costs
+                }
             }
             for (int j = lane; j <= m; j += 32) {
                 if (used[j]) { u[p[j]] += delta; v[j] -= delta; }
@@ -144,8 +151,17 @@ group_lsa_kernel(const float *__restrict__ cost, const ImageTable tab, const int
 
 extern "C" {
 
+int detr_group_lsa_status_f32(const float *cost, const int *sizes, int B, int Q, int T, int groups, int64_t *out_query,
+                              int64_t *out_target, int *status, void *stream);
+
 int detr_group_lsa_f32(const float *cost, const int *sizes, int B, int Q, int T, int groups, int64_t *out_query,
                        int64_t *out_target, void *stream)
+{
+    return detr_group_lsa_status_f32(cost, sizes, B, Q, T, groups, out_query, out_target, nullptr, stream);
+}
+
+int detr_group_lsa_status_f32(const float *cost, const int *sizes, int B, int Q, int T, int groups, int64_t *out_query,
+                              int64_t *out_target, int *status, void *stream)
 {
     if (B < 0 || Q < 0 || T < 0 || groups < 1 || Q % groups != 0)
         return fail(DETR_STEP_ERR_BAD_SHAPE, "detr_group_lsa_f32: bad shape (B=%d Q=%d T=%d groups=%d)", B, Q, T, groups);
@@ -171,7 +187,7 @@ int detr_group_lsa_f32(const float *cost, const int *sizes, int B, int Q, int T,
     if (smem > 48 * 1024)
         return fail(DETR_STEP_ERR_UNSUPPORTED, "detr_group_lsa_f32: sub-problem %d x %d needs %zu B of shared memory", nmax, mmax, smem);
     group_lsa_kernel<<<(unsigned)(B * groups), 32, smem, (cudaStream_t)stream>>>(cost, tab, Q, T, groups, nmax, mmax,
-                                                                               out_query, out_target);
+                                                                               out_query, out_target, status);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(t_err, sizeof(t_err), "detr_group_lsa_f32: %s (cudaError %d)", cudaGetErrorString(e), (int)e);

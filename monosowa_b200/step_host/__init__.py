@@ -14,5 +14,5 @@ and the MSDA operator (monosowa_b200.ops) is independent of this module.
 from __future__ import annotations
 
 from .lsa import group_lsa  # noqa: F401
-from .patches import (DeviceMatcher, foreach_adamw_step, install, paint_depth_targets, paint_foreground,  # noqa: F401
-                      pairwise_l1)
+from .patches import (DeviceMatcher, foreach_adamw_step, fuse_dense_attention, install, paint_depth_targets,  # noqa: F401
+                      paint_foreground, pairwise_l1)

@@ -23,9 +23,49 @@ def lib() -> ctypes.CDLL:
         handle = ctypes.CDLL(LIB_PATH)
         handle.detr_group_lsa_f32.restype = ctypes.c_int
         handle.detr_group_lsa_f32.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 3
+        handle.detr_group_lsa_status_f32.restype = ctypes.c_int
+        handle.detr_group_lsa_status_f32.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4
         handle.detr_step_last_error.restype = ctypes.c_char_p
         _lib = handle
     return _lib
+
+
+class _Status:
+    """Non-finite-cost flag of the matching kernel, read WITHOUT adding a synchronisation to the step: the device flag is
+    copied to pinned host memory behind the kernel and looked at when the next call arrives (by then the copy of the
+    previous call has long completed).  scipy.optimize.linear_sum_assignment raises ValueError on NaN / Inf costs
+    (reference matcher.py:101); so does this, one matcher call late."""
+
+    def __init__(self, device):
+        self.dev = torch.zeros(1, dtype=torch.int32, device=device)
+        self.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.event = None
+
+    def check(self, wait=False):
+        if self.event is not None and (wait or self.event.query()):
+            if wait:
+                self.event.synchronize()
+            self.event = None
+            if int(self.host[0]) != 0:
+                self.host.zero_()
+                self.dev.zero_()
+                raise ValueError("matrix contains invalid numeric entries (NaN or Inf in the matching cost of an earlier "
+                                 "call: the device matcher reports it when it is next used)")
+
+    def arm(self):
+        self.host.copy_(self.dev, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+
+_status: dict = {}
+
+
+def check_status(device=None, wait=True):
+    """raise now if a matching call on `device` (default: every device used so far) saw non-finite costs"""
+    for dev, st in _status.items():
+        if device is None or torch.device(device) == dev:
+            st.check(wait=wait)
 
 
 def group_lsa(cost: torch.Tensor, sizes, groups: int):
@@ -48,9 +88,16 @@ def group_lsa(cost: torch.Tensor, sizes, groups: int):
     out_t = torch.empty(total, dtype=torch.int64, device=cost.device)
     if total:
         with torch.cuda.device(cost.device):
-            rc = lib().detr_group_lsa_f32(ctypes.c_void_p(cost.data_ptr()), (ctypes.c_int * B)(*sizes), B, Q, T, groups,
-                                          ctypes.c_void_p(out_q.data_ptr()), ctypes.c_void_p(out_t.data_ptr()),
-                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            st = _status.get(cost.device)
+            if st is None:
+                st = _status[cost.device] = _Status(cost.device)
+            st.check()                                                       # an earlier call's verdict, if it has arrived
+            rc = lib().detr_group_lsa_status_f32(ctypes.c_void_p(cost.data_ptr()), (ctypes.c_int * B)(*sizes), B, Q, T, groups,
+                                                 ctypes.c_void_p(out_q.data_ptr()), ctypes.c_void_p(out_t.data_ptr()),
+                                                 ctypes.c_void_p(st.dev.data_ptr()),
+                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            if rc == 0:
+                st.arm()
         if rc == ERR_UNSUPPORTED:
             return None
         if rc:

@@ -213,9 +213,46 @@ def _counts(per_image, device):
     return t
 
 
-def install(criterion=None, optimizer=None, matcher=True, ddn=True, adamw=True):
+def fuse_dense_attention(model):
+    """the decoder's two dense attentions -- depth cross-attention (550 queries x 1920 depth
+    positions) and the grouped self-attention (reference depthaware_transformer.py:455-503) -- are
+    ``nn.MultiheadAttention`` modules called as ``mha(q, k, v, ...)[0]``: the averaged attention weights they return
+    by default are thrown away, but asking for them forces PyTorch onto the path that materialises the
+    (N*heads, Lq, Lk) probability matrix (540 MB in fp32 for the depth attention at batch 16) in forward and backward.
+    With ``need_weights=False`` the same module computes the same output through the fused
+    ``scaled_dot_product_attention`` kernels (library code: it stays cuDNN / PyTorch's, this only selects it).
+    Returns the number of modules patched.  Outputs agree to fp32 rounding (tests/test_step_host.py); with dropout
+    active both paths drop attention probabilities with p = module.dropout, from different random streams.
+
+    MEASURED on B200 (profiles/r02_training_step.md): in fp32 -- the reference's precision -- this is a LOSS.  PyTorch
+    2.11 has no flash kernel for fp32; SDPA falls to the sm80 SIMT memory-efficient kernels
+    (fmha_cutlassF/B_f32_aligned_64x64), 7.1 + 17.0 ms per step against ~5 ms for the materialising path, and the step
+    goes from 158.7 to 161.7 ms.  It pays only under bf16 autocast.  Hence opt-in (install(..., attention=True),
+    --host-opt all,sdpa), not part of the default set."""
+    n = 0
+    for layer in model.modules():
+        for name in ("cross_attn_depth", "self_attn"):
+            mha = getattr(layer, name, None)
+            if isinstance(mha, torch.nn.MultiheadAttention) and not getattr(mha, "_msda_fused_sdpa", False):
+                orig = mha.forward
+
+                def fwd(query, key, value, *args, _orig=orig, **kw):
+                    if len(args) >= 2:                            # need_weights passed positionally: leave the call alone
+                        return _orig(query, key, value, *args, **kw)
+                    kw["need_weights"] = False
+                    return _orig(query, key, value, *args, **kw)
+
+                mha.forward = fwd
+                mha._msda_fused_sdpa = True
+                n += 1
+    return n
+
+
+def install(criterion=None, optimizer=None, matcher=True, ddn=True, adamw=True, model=None, attention=False):
     """Attach the device-resident sections to live reference objects; returns the names of what was installed."""
     done = []
+    if model is not None and attention and fuse_dense_attention(model):
+        done.append("sdpa")
     if criterion is not None and matcher and hasattr(criterion, "matcher"):
         dm = DeviceMatcher(criterion.matcher)
         criterion.matcher.forward = dm                            # nn.Module.__call__ dispatches to the instance attribute

@@ -201,5 +201,25 @@ def test_bench_reference_arm_contract():
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "GB/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    staged = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "MonoDETR", "lib", "models", "monodetr", "ops",
+                                         "functions", "ms_deform_attn_func.py"))
+    # the reference's own function when the tree is staged (baseline/_ref), the oracle's restatement of it otherwise
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"].startswith("BASELINE.json configs[1]")
+    assert line["native_libraries_loaded"] == [], "the reference arm must not load the product library"
+
+
+def test_reference_arm_function_is_the_oracles_restatement():
+    """bench.py --impl reference times the staged reference's ms_deform_attn_core_pytorch; the oracle restates the same
+    function: on the same inputs they must agree bit for bit (both are grid_sample on this torch build)"""
+    import bench
+    from oracle import msda_oracle as O
+    core = bench.load_reference_core()
+    if core is None:
+        pytest.skip("baseline/_ref/MonoDETR not staged")
+    g = torch.Generator().manual_seed(3)
+    sh = torch.tensor([[6, 4], [3, 2]])
+    value = torch.rand(2, 30, 2, 8, generator=g)
+    loc = torch.rand(2, 5, 2, 2, 3, 2, generator=g) * 1.4 - 0.2
+    attn = torch.softmax(torch.rand(2, 5, 2, 6, generator=g), -1).view(2, 5, 2, 2, 3)
+    assert torch.equal(core(value, sh, loc, attn), O.core_grid_sample(value, sh, loc, attn))

@@ -197,7 +197,7 @@ def test_step_library_exports_declared_symbols():
     from monosowa_b200.step_host import lsa
     hdr = open(os.path.join(ROOT, "include", "monodetr_step_b200.h")).read()
     declared = set(re.findall(r"\b(detr_[a-z0-9_]+)\s*\(", hdr))
-    assert declared == {"detr_group_lsa_f32", "detr_step_last_error"}
+    assert declared == {"detr_group_lsa_f32", "detr_group_lsa_status_f32", "detr_step_last_error"}
     raw = ctypes.CDLL(lsa.LIB_PATH) if os.path.exists(lsa.LIB_PATH) else lsa.lib()
     for name in declared:
         assert hasattr(raw, name)
@@ -240,6 +240,30 @@ def test_group_lsa_matches_scipy(cuda_device, case):
     for (gq, gt), (wq, wt) in zip(got, want):
         assert gq.dtype == torch.int64 and gq.is_cuda
         assert torch.equal(gq.cpu(), wq) and torch.equal(gt.cpu(), wt)
+
+
+@pytest.mark.gpu
+def test_group_lsa_reports_non_finite_costs_like_scipy(cuda_device):
+    """scipy.optimize.linear_sum_assignment raises ValueError on NaN / Inf costs (reference matcher.py:101), which stops
+    a diverged run; the device matcher raises the same error -- when the flag copied behind the kernel has arrived,
+    i.e. at the next call or at an explicit check_status()"""
+    from scipy.optimize import linear_sum_assignment
+    from monosowa_b200.step_host import lsa
+    cost = torch.rand(2, 20, 12, device=cuda_device)
+    assert lsa.group_lsa(cost, [5, 7], 2) is not None
+    lsa.check_status()                                           # finite costs: nothing to report
+    bad = cost.clone()
+    bad[1, :, 5:] = float("nan")                                 # every cost of image 1 is NaN
+    with pytest.raises(ValueError):
+        linear_sum_assignment(bad[1, :10, 5:].cpu())
+    lsa.group_lsa(bad, [5, 7], 2)                                # returns (no synchronisation inside the call) ...
+    with pytest.raises(ValueError, match="invalid numeric entries"):
+        lsa.check_status()                                       # ... and the verdict follows
+    lsa.check_status()                                           # reported once
+    lsa.group_lsa(bad, [5, 7], 2)
+    torch.cuda.synchronize()
+    with pytest.raises(ValueError, match="invalid numeric entries"):
+        lsa.group_lsa(cost, [5, 7], 2)                           # the next call raises for the previous one
 
 
 @pytest.mark.gpu
@@ -302,3 +326,63 @@ def test_device_matcher_matches_reference_matcher(cuda_device):
     got = DeviceMatcher(matcher)(outputs, targets, group_num=11)
     for (gq, gt), (wq, wt) in zip(got, want):
         assert torch.equal(gq.cpu(), wq) and torch.equal(gt.cpu(), wt)
+
+
+# ------------------------------------------------------------------------------------------------
+# the decoder's dense attentions through fused SDPA (step_host.fuse_dense_attention)
+# ------------------------------------------------------------------------------------------------
+class _Layer(torch.nn.Module):
+    """the two attention members of the reference's DepthAwareDecoderLayer (depthaware_transformer.py:399, 404)"""
+
+    def __init__(self, d_model=256, heads=8, dropout=0.0):
+        super().__init__()
+        self.cross_attn_depth = torch.nn.MultiheadAttention(d_model, heads, dropout=dropout)
+        self.self_attn = torch.nn.MultiheadAttention(d_model, heads, dropout=dropout)
+        self.other = torch.nn.MultiheadAttention(d_model, heads, dropout=dropout)      # not one of the two: left alone
+
+
+def test_fuse_dense_attention_patches_exactly_the_two_decoder_attentions():
+    from monosowa_b200 import step_host
+    layer = _Layer(32, 4)
+    assert step_host.fuse_dense_attention(torch.nn.Sequential(layer)) == 2
+    assert step_host.fuse_dense_attention(torch.nn.Sequential(layer)) == 0          # idempotent
+    q, kv = torch.randn(5, 2, 32), torch.randn(7, 2, 32)
+    out, w = layer.cross_attn_depth(q, kv, kv, key_padding_mask=torch.zeros(2, 7, dtype=torch.bool))
+    assert w is None and out.shape == (5, 2, 32)                                      # the reference only uses [0]
+    assert layer.other(q, kv, kv)[1] is not None
+    ref = torch.nn.MultiheadAttention(32, 4)
+    ref.load_state_dict(layer.cross_attn_depth.state_dict())
+    assert torch.allclose(out, ref(q, kv, kv)[0], atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_fused_sdpa_matches_the_unmodified_attention_layers(cuda_device):
+    """depth cross-attention at the training shape (550 queries x 1920 depth positions, batch 16, key padding mask) and
+    the grouped self-attention shape (50 x 50, batch 16 * 11 groups): outputs rel-L2 <= 1e-5, gradients <= 1e-4"""
+    from monosowa_b200 import step_host
+    dev = cuda_device
+    torch.manual_seed(5)
+    plain, fused = _Layer().to(dev), _Layer().to(dev)
+    fused.load_state_dict(plain.state_dict())
+    assert step_host.fuse_dense_attention(fused) == 2
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()
+    for name, lq, lk, n, masked in (("cross_attn_depth", 550, 1920, 16, True), ("self_attn", 50, 50, 176, False)):
+        q = torch.randn(lq, n, 256, device=dev, requires_grad=True)
+        k = torch.randn(lk, n, 256, device=dev, requires_grad=True)
+        mask = None
+        if masked:
+            mask = torch.zeros(n, lk, dtype=torch.bool, device=dev)
+            mask[:, -80:] = True                                   # a padded bottom strip of the depth map
+        g = torch.randn(lq, n, 256, device=dev)
+        res = []
+        for layer in (plain, fused):
+            for t in (q, k):
+                t.grad = None
+            layer.zero_grad()
+            mha = getattr(layer, name)
+            out = mha(q, k, k, key_padding_mask=mask)[0]
+            out.backward(g)
+            res.append((out.detach(), q.grad.clone(), k.grad.clone(), mha.in_proj_weight.grad.clone()))
+        assert rel(res[1][0], res[0][0]) < 1e-5, name
+        for a, b in zip(res[1][1:], res[0][1:]):
+            assert rel(a, b) < 1e-4, name

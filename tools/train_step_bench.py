@@ -115,8 +115,9 @@ def make_parser():
     ap.add_argument("--logging", default="faithful", choices=["faithful", "lean"])
     ap.add_argument("--profile-msda", action="store_true", help="kineto pass: MSDA kernels' share of the step")
     ap.add_argument("--host-opt", default="none",
-                    help="SURVEY 8 f3: comma list of matcher,ddn,adamw or 'all' -- device-resident replacements of the "
-                         "step's host sections (monosowa_b200.step_host); 'none' = the reference's own code")
+                    help="SURVEY 8 f3/f4: comma list of matcher,ddn,adamw,sdpa or 'all' -- device-resident replacements of the "
+                         "step's host sections and fused SDPA for the decoder's dense attentions (monosowa_b200.step_host); "
+                         "'none' = the reference's own code")
     ap.add_argument("--ddp", default="lean", choices=["default", "lean"],
                     help="lean: static_graph (the unused-parameter search runs once, not every step) and no per-step "
                          "buffer broadcast (the only buffers are FrozenBatchNorm statistics, which never change)")
@@ -174,11 +175,16 @@ def run(args):
     host_opt, host_opt_check = [], None
     if args.host_opt != "none":
         from monosowa_b200 import step_host
-        want = {"matcher", "ddn", "adamw"} if args.host_opt == "all" else set(args.host_opt.split(","))
+        # "all" = what pays: fused SDPA for the dense attentions is an opt-in ("all,sdpa"): measured SLOWER in fp32 on B200
+        # (PyTorch's only fp32 fused kernel is the sm80 SIMT memory-efficient one: 24 vs ~5 ms per step, profiles/r02_training_step.md)
+        want = set(args.host_opt.split(","))
+        if "all" in want:
+            want |= {"matcher", "ddn", "adamw"}
         with torch.no_grad():                               # same model outputs through the reference criterion ...
             out0 = model(images, calibs, targets, tdict["img_size"], dn_args=None)
             ld_ref = {k: float(v) for k, v in criterion(out0, targets, None, None).items()}
-        host_opt = step_host.install(criterion, optimizer, matcher="matcher" in want, ddn="ddn" in want, adamw="adamw" in want)
+        host_opt = step_host.install(criterion, optimizer, matcher="matcher" in want, ddn="ddn" in want, adamw="adamw" in want,
+                                     model=model, attention="sdpa" in want)
         with torch.no_grad():                               # ... and through the patched one: every loss term must agree
             ld_opt = {k: float(v) for k, v in criterion(out0, targets, None, None).items()}
         host_opt_check = {"loss_terms": len(ld_ref), "max_abs_diff": max(abs(ld_ref[k] - ld_opt[k]) for k in ld_ref),
