@@ -410,10 +410,18 @@ def run_ours(args, wl):
     chk = chk and (torch.equal(host_out[0].to(dev), out) if rank == 0 else True)   # both e2e paths reproduce the device forward
 
     ref_cuda = time_reference_cuda(d, ab, args) if (world == 1 and rank == 0 and not args.no_ref_cuda) else None
+    # configs[2] / configs[4] on every rank (configs[4] is "at 8 B200": one replica per GPU, no collective in the data
+    # path); per-row times are the slowest rank's, GB/s is the whole job's
     other = None
-    if world == 1 and not args.no_other_configs:
+    if not args.no_other_configs:
         try:
             other = other_configs_table(msda, W, dev)
+            if use_dist:
+                t = torch.tensor([[r["fwd_us"], r["bwd_us"]] for r in other], dtype=torch.float64)
+                t = reduce_fn(t, "max")
+                for r, (f_us, b_us) in zip(other, t.tolist()):
+                    r["GBps"] = round(r["GBps"] * (r["fwd_us"] + r["bwd_us"]) / (f_us + b_us) * world, 1)
+                    r["fwd_us"], r["bwd_us"], r["replicas"] = round(f_us, 1), round(b_us, 1), world
         except Exception as exc:  # noqa: BLE001
             other = [{"unavailable": repr(exc)[:200]}]
 

@@ -968,3 +968,27 @@ def test_module_bf16_autocast_trains(msda, cuda_device):
     out16.float().pow(2).mean().backward()
     assert q.grad is not None and src.grad is not None and torch.isfinite(src.grad).all()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in mod.parameters())
+
+
+# --------------------------------------------------------------------------------------------
+# 8. the measurement build (libmsda_b200_ab.so, -DMSDA_AB): tile kernels, kept correct although not shipped
+# --------------------------------------------------------------------------------------------
+def test_measurement_build_suite_in_a_child_process(msda):
+    """The tile kernels exist only in the measurement build, which is loaded instead of the product
+    library when MSDA_AB=1.  A process has one library, so their cases -- skipped above -- run in a child process."""
+    import os
+    import subprocess
+    import sys
+    from monosowa_b200 import build as B
+    if msda._lib.has_ab_flavours():
+        pytest.skip("already running against the measurement build")
+    if not os.path.exists(B.AB_LIB):
+        pytest.skip("libmsda_b200_ab.so not built (python -m monosowa_b200.build --ab)")
+    env = dict(os.environ, MSDA_AB="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "long_query or every_launch_variant or fused_preprocessing or guard_bands or nan_behind"],
+                       capture_output=True, text=True, timeout=1500, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in tail and "skipped" not in tail, tail
+
