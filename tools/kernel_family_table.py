@@ -1,6 +1,13 @@
-import sys, os, json, torch
-sys.path.insert(0, "/root/repo")
-import monosowa_b200 as msda
+"""Shipped default vs record kernels vs tile kernels (measurement build: MSDA_AB=1) on configs[1] and the configs[4]
+shapes:   MSDA_AB=1 python tools/kernel_family_table.py > gpurun_out/kernel_family_table.jsonl"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import monosowa_b200 as msda  # noqa: E402
 from monosowa_b200 import workloads as W
 from tools.sweep import timeit
 dev = torch.device("cuda:0")
