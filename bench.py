@@ -368,7 +368,8 @@ def run_ours(args, wl):
 
     def step_host():
         msda.host_step(host_in["value"], d["shapes"], d["lsi"], host_in["loc"], host_in["attn"], go_host,
-                       images_per_chunk=args.e2e_images_per_chunk, results=tuple(host_out), synchronize=False)
+                       images_per_chunk=args.e2e_images_per_chunk, results=tuple(host_out), synchronize=False,
+                       stages=args.e2e_stages)
 
     e2e_ms = time_e2e(step_host)
     chk = torch.equal(host_out[0].to(dev), out) if rank == 0 else True
@@ -467,7 +468,7 @@ def run_ours(args, wl):
                 "d2h_bytes_per_step": d2h_bytes * world, "bytes_note": "whole job (all ranks), like `value`", "chunks": chunks, "matches_device_path": out_shape_checked, "pcie": pcie,
                 "frac_of_pcie_floor": (pcie["duplex_ms"] / e2e_ms_max) if pcie else None,
                 "api": "msda_host_step_f32 (C ABI, pinned host buffers in and out; monosowa_b200.host_step), "
-                       f"{args.e2e_images_per_chunk} image(s) per pipeline chunk",
+                       f"{args.e2e_images_per_chunk} image(s) per pipeline chunk, {args.e2e_stages} stages",
                 "autograd_api_ms_per_step": e2e_autograd_ms,
                 "autograd_api": f"MSDeformAttnFunction.apply + autograd, Python 3-stream pipeline, {chunks} chunks"},
         "gpu_launches": int(launches),
@@ -652,6 +653,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--e2e-images-per-chunk", type=int, default=1)
+    ap.add_argument("--e2e-stages", type=int, default=3, help="device stages of the host-step pipeline (3..16)")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")

@@ -152,8 +152,10 @@ int msda_backward_fused_bf16(const void *value, const int64_t *spatial_shapes,
  * caller with host data pays cudaMemcpy + kernels + cudaMemcpy serially.  Here the batch is pipelined
  * in chunks of `images_per_chunk` images (images are independent, cuh:269) over two internal copy
  * streams and `stream`: H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap.
- *   workspace : DEVICE scratch of at least msda_host_step_workspace_bytes(...) bytes, 256-byte
- *               aligned, owned by the caller (the library never allocates device memory).
+ *   workspace : DEVICE scratch of at least msda_host_step_workspace_bytes(...) bytes (three pipeline
+ *               stages), 256-byte aligned, owned by the caller (the library never allocates device
+ *               memory).  A larger workspace is used for a deeper ring, up to 16 stages (whole
+ *               multiples of a third of the minimum): worth it when H2D and D2H run at different paces.
  * Nothing blocks the host; results are valid once `stream` has been synchronised.  The copy streams
  * are per device: calls on one device are serialised by that device's mutex and each call waits for the
  * previous call's last copy, so calls from different caller streams need SEPARATE workspaces only if they

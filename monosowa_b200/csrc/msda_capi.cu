@@ -151,15 +151,18 @@ static int fused_impl(const char *fn, DType dt, bool backward, const void *value
 // step").  Images are independent (the value index is prefixed by n, reference cuh:269), so the batch is
 // pipelined in chunks of whole images over two internal copy streams and the caller's stream:
 //   s_in : H2D of chunk i+1     |  stream : forward + backward of chunk i  |  s_out : D2H of chunk i-1
-// through a ring of kHostStages device stages carved from the caller's workspace.  Nothing here blocks
+// through a ring of device stages carved from the caller's workspace: kHostStages (3) at least, as many more as the
+// workspace holds (up to kHostStagesMax) -- a deeper ring lets the H2D side run ahead when the two directions do not
+// proceed at the same pace (8 GPUs behind one host fabric: profiles/r02_n8_e2e_stages.txt).  Nothing here blocks
 // the host; the caller synchronises `stream` before reading the results.
 constexpr int kHostStages = 3;
+constexpr int kHostStagesMax = 16;
 
 struct HostPipe {
     std::mutex mu;                  // serialises the calls of one device (they share the copy streams)
     bool ready = false, has_prev = false;
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t start = nullptr, done = nullptr, in[kHostStages] = {}, cmp[kHostStages] = {}, out[kHostStages] = {};
+    cudaEvent_t start = nullptr, done = nullptr, in[kHostStagesMax] = {}, cmp[kHostStagesMax] = {}, out[kHostStagesMax] = {};
 };
 static HostPipe g_pipe[64];
 
@@ -199,7 +202,7 @@ static void host_pipe_destroy(HostPipe &p)
     if (p.s_out) cudaStreamDestroy(p.s_out);
     if (p.start) cudaEventDestroy(p.start);
     if (p.done) cudaEventDestroy(p.done);
-    for (int i = 0; i < kHostStages; ++i) {
+    for (int i = 0; i < kHostStagesMax; ++i) {
         if (p.in[i]) cudaEventDestroy(p.in[i]);
         if (p.cmp[i]) cudaEventDestroy(p.cmp[i]);
         if (p.out[i]) cudaEventDestroy(p.out[i]);
@@ -218,7 +221,7 @@ static int host_pipe_prepare(HostPipe &p)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming);
-    for (int i = 0; i < kHostStages && e == cudaSuccess; ++i) {
+    for (int i = 0; i < kHostStagesMax && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&p.in[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.cmp[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.out[i], cudaEventDisableTiming);
@@ -253,6 +256,8 @@ static int host_step_impl(const char *fn, DType dt, const void *h_value, const i
     if (workspace_bytes < (size_t)kHostStages * lay.total || !aligned(workspace, 256))
         return fail(MSDA_ERR_BAD_SHAPE, "%s: workspace too small or not 256-byte aligned (%zu bytes needed)", fn,
                     (size_t)kHostStages * lay.total);
+    const size_t fit = lay.total ? workspace_bytes / lay.total : (size_t)kHostStagesMax;
+    const int stages = (int)(fit < (size_t)kHostStagesMax ? fit : (size_t)kHostStagesMax);
     int dev = 0;
     MSDA_CU(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return cuda_result((int)cudaErrorInvalidDevice, fn);
@@ -273,9 +278,9 @@ static int host_step_impl(const char *fn, DType dt, const void *h_value, const i
     int chunk = 0;
     for (int n0 = 0; n0 < N; n0 += cb, ++chunk) {
         const int nb = (N - n0 < cb) ? N - n0 : cb;
-        const int s = chunk % kHostStages;
+        const int s = chunk % stages;
         char *base = (char *)workspace + (size_t)s * lay.total;
-        if (chunk >= kHostStages) MSDA_CU(cudaStreamWaitEvent(p.s_in, p.out[s], 0));          // stage drained
+        if (chunk >= stages) MSDA_CU(cudaStreamWaitEvent(p.s_in, p.out[s], 0));               // stage drained
         MSDA_CU(cudaMemcpyAsync(base + lay.value, (const char *)h_value + n0 * vb, nb * vb, cudaMemcpyHostToDevice, p.s_in));
         MSDA_CU(cudaMemcpyAsync(base + lay.loc, (const char *)h_loc + n0 * lb, nb * lb, cudaMemcpyHostToDevice, p.s_in));
         MSDA_CU(cudaMemcpyAsync(base + lay.attn, (const char *)h_attn + n0 * ab, nb * ab, cudaMemcpyHostToDevice, p.s_in));

@@ -36,7 +36,7 @@ def release_workspaces() -> None:
 
 
 def host_step(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, grad_output,
-              images_per_chunk: int = 1, results=None, synchronize: bool = True):
+              images_per_chunk: int = 1, results=None, synchronize: bool = True, stages: int = 3):
     dev = spatial_shapes.device
     if dev.type != "cuda" or level_start_index.device != dev:
         raise NotImplementedError("spatial_shapes / level_start_index must be CUDA tensors: they select the device "
@@ -79,9 +79,10 @@ def host_step(value, spatial_shapes, level_start_index, sampling_locations, atte
     ptr = lambda t: ctypes.c_void_p(t.data_ptr())
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream()
-        ws = _workspace(dev, stream.cuda_stream, max(need, 256))
+        ws_bytes = max(need // 3 * max(3, min(int(stages), 16)), 256)          # `need` = the minimum: 3 stages
+        ws = _workspace(dev, stream.cuda_stream, ws_bytes)
         rc = fn(ptr(value), ptr(spatial_shapes), ptr(level_start_index), ptr(sampling_locations), ptr(attention_weights),
-                ptr(grad_output), ptr(out), ptr(gv), ptr(gl), ptr(ga), ptr(ws), ctypes.c_size_t(ws.numel()),
+                ptr(grad_output), ptr(out), ptr(gv), ptr(gl), ptr(ga), ptr(ws), ctypes.c_size_t(ws_bytes),
                 n, s, m, d, nl, lq, p, int(images_per_chunk), ctypes.c_void_p(stream.cuda_stream))
         if rc:
             raise RuntimeError(f"msda_host_step failed (code {rc}): {_lib.last_error()}")

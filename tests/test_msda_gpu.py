@@ -726,10 +726,10 @@ def test_host_buffer_step_matches_device_path(msda, cuda_device, dtype, per_chun
     assert not out.is_cuda and out.dtype == dtype and gv.dtype == dtype
     assert torch.equal(out, want[0]) and torch.equal(gl, want[2]) and torch.equal(ga, want[3])
     assert O.rel_l2(gv, want[1]) < (1e-5 if dtype == torch.float32 else 1e-2)
-    # a second call reuses the cached workspace and the caller's result buffers
+    # a second call reuses the cached workspace and the caller's result buffers; a deeper ring (5 stages) changes nothing
     res2 = msda.host_step(v.pin_memory(), sh.to(dev), lsi.to(dev), l.pin_memory(), a.pin_memory(),
-                          g.reshape(N, Lq, M * D).pin_memory(), images_per_chunk=per_chunk, results=(out, gv, gl, ga))
-    assert res2[0] is out and torch.equal(out, want[0])
+                          g.reshape(N, Lq, M * D).pin_memory(), images_per_chunk=per_chunk, results=(out, gv, gl, ga), stages=5)
+    assert res2[0] is out and torch.equal(out, want[0]) and torch.equal(gl, want[2])
     with pytest.raises(RuntimeError):
         msda.host_step(v.to(dev), sh.to(dev), lsi.to(dev), l, a, g.reshape(N, Lq, M * D))       # device tensor: wrong entry point
     with pytest.raises(NotImplementedError):
