@@ -12,7 +12,8 @@
 //     recomputed it in all 8 lanes and was instruction-issue bound (profiles/r01_v1_*);
 //   * samples outside the sampling window are compacted away before the gather loop (they cost
 //     neither loads nor FMAs, and -- like the reference's branch, cuh:288 -- never touch `value`);
-//   * long query sets run a persistent grid over 2-D image tiles (msda_tiles.cuh): fwd_tile_kernel.
+//   * (measurement build only, -DMSDA_AB) fwd_tile_kernel: a persistent grid over 2-D image tiles (msda_tiles.cuh) --
+//     built in round 2, parity-green, slower than the record kernel (see use_tile below, profiles/r02_tile_kernels.md).
 // The op is a gather: no tensor cores; the bound is 128-byte rows through the L1 data pipe.
 #include "msda_common.cuh"
 #include "msda_records.cuh"

@@ -1,4 +1,5 @@
 // msda_tiles.cuh -- query tiles for long query sets (the encoder: queries ARE the pixel pyramid).
+// Used by the tile kernels of the measurement build only (-DMSDA_AB; DESIGN.md 4.3, profiles/r02_tile_kernels.md).
 //
 // Why: both directions of the op are bound by 128-byte ROWS moved between L2 and the SMs,
 // not by HBM.  In MonoDETR's encoder (reference depthaware_transformer.py:363-376) query q is pixel q of the

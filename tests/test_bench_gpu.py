@@ -1,0 +1,38 @@
+"""bench.py keeps its contract with the driver: one JSON line with the agreed keys (BASELINE.json metric, roofline with
+the binding-unit ceiling, cpu_baseline, e2e with declared copies, gpu_launches = the launches of the timed region)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def test_bench_line_contract(cuda_device):
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--sustain-steps", "3",
+           "--cpu-steps", "1", "--no-train-step", "--no-other-configs"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [x for x in r.stdout.strip().splitlines() if x.startswith("{")]
+    assert len(lines) == 1, "exactly one JSON line on stdout"
+    d = json.loads(lines[0])
+    assert d["metric"] == "MSDA fwd+bwd GB/s" and d["unit"] == "GB/s" and d["n_gpus"] == 1 and d["steps"] == 3
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f32"
+    assert d["config"]["workload"].startswith("BASELINE.json configs[1]") and d["data"] == "synthetic"
+    assert d["value"] > 300 and abs(d["value"] - d["value_sustained"]) / d["value"] < 0.2
+    assert d["gpu_launches"] == 6, "3 timed steps = 3 forward + 3 backward launches of libmsda_b200.so"
+    assert d["kernels"] == {"fwd": "fwd_rec_f32", "bwd": "bwd_bin_f32"}
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["kernel"] == "bwd" and rf["unit"] == "GB/s" and rf["traffic"] > 0
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 0.03 < rf["frac"] < 0.6
+    c = rf["binding_ceiling"]
+    assert c["live_rows_per_launch"] > 6e7 and c["fwd_plus_bwd_floor_ms"] > 1.0 and 0.3 < rf["frac_of_binding_ceiling"] < 1.0
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == e["d2h_bytes_per_step"] == 584908800 and e["matches_device_path"] is True
+    assert 0 < e["value"] < d["value"] and e["pcie"]["ranks_copying_at_once"] == 1 and 0.3 < e["frac_of_pcie_floor"] <= 1.05
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and cb["unit"] == "GB/s"
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
