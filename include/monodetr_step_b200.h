@@ -55,6 +55,19 @@ int detr_group_lsa_f32(const float *cost, const int *sizes, int B, int Q, int T,
 int detr_group_lsa_status_f32(const float *cost, const int *sizes, int B, int Q, int T, int groups,
                               int64_t *out_query, int64_t *out_target, int *status, void *stream);
 
+/* FrozenBatchNorm2d (+ residual add) (+ ReLU) in one pass over a contiguous NCHW fp32 activation of `n` elements
+ * (`hw` = H*W, `C` channels): replaces the element-wise kernels behind MonoDETR/lib/models/monodetr/backbone.py:55-65
+ * (`x * scale + bias`) and torchvision's Bottleneck tail (`out += identity; relu(out)`).
+ *   y = relu?( fadd( fadd( fmul(x, scale[c]), bias[c] ), residual? ) )     every step rounded, the reference's order:
+ * results are bit-identical to the separate kernels.  `residual` may be NULL, `relu` is 0 / 1.
+ * Backward: grad_x = fmul(m, scale[c]), grad_residual (may be NULL) = m, with m = grad_y where y > 0 (relu) else grad_y;
+ * `y` is only read when relu != 0.  scale / bias are frozen buffers: no gradient.  Return 0, a negative
+ * DETR_STEP_ERR_* code, or a cudaError_t from the launch. */
+int detr_frozen_bn_act_f32(const float *x, const float *residual, const float *scale, const float *bias, float *y,
+                           long long n, long long hw, int C, int relu, void *stream);
+int detr_frozen_bn_act_backward_f32(const float *grad_y, const float *y, const float *scale, float *grad_x,
+                                    float *grad_residual, long long n, long long hw, int C, int relu, void *stream);
+
 const char *detr_step_last_error(void);
 
 #ifdef __cplusplus

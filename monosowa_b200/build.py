@@ -26,7 +26,7 @@ HEADERS = [os.path.join(CSRC, "msda_common.cuh"), os.path.join(CSRC, "msda_recor
            os.path.join(ROOT, "include", "monodetr_step_b200.h")]
 # second library: device-side pieces of the MonoDETR training step, kept out of the operator's ABI
 STEP_LIB = os.path.join(PKG, "libmonodetr_step_b200.so")
-STEP_SOURCES = ["step_lsa.cu"]
+STEP_SOURCES = ["step_lsa.cu", "step_bn.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,

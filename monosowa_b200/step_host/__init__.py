@@ -16,3 +16,4 @@ from __future__ import annotations
 from .lsa import group_lsa  # noqa: F401
 from .patches import (DeviceMatcher, foreach_adamw_step, fuse_dense_attention, install, paint_depth_targets,  # noqa: F401
                       paint_foreground, pairwise_l1)
+from .frozen_bn import frozen_bn_act, fuse_frozen_bn  # noqa: F401

@@ -248,9 +248,13 @@ def fuse_dense_attention(model):
     return n
 
 
-def install(criterion=None, optimizer=None, matcher=True, ddn=True, adamw=True, model=None, attention=False):
+def install(criterion=None, optimizer=None, matcher=True, ddn=True, adamw=True, model=None, attention=False, frozen_bn=True):
     """Attach the device-resident sections to live reference objects; returns the names of what was installed."""
     done = []
+    if model is not None and frozen_bn:
+        from .frozen_bn import fuse_frozen_bn
+        if fuse_frozen_bn(model):
+            done.append("frozen_bn")
     if model is not None and attention and fuse_dense_attention(model):
         done.append("sdpa")
     if criterion is not None and matcher and hasattr(criterion, "matcher"):

@@ -197,7 +197,8 @@ def test_step_library_exports_declared_symbols():
     from monosowa_b200.step_host import lsa
     hdr = open(os.path.join(ROOT, "include", "monodetr_step_b200.h")).read()
     declared = set(re.findall(r"\b(detr_[a-z0-9_]+)\s*\(", hdr))
-    assert declared == {"detr_group_lsa_f32", "detr_group_lsa_status_f32", "detr_step_last_error"}
+    assert declared == {"detr_group_lsa_f32", "detr_group_lsa_status_f32", "detr_frozen_bn_act_f32",
+                        "detr_frozen_bn_act_backward_f32", "detr_step_last_error"}
     raw = ctypes.CDLL(lsa.LIB_PATH) if os.path.exists(lsa.LIB_PATH) else lsa.lib()
     for name in declared:
         assert hasattr(raw, name)
@@ -386,3 +387,104 @@ def test_fused_sdpa_matches_the_unmodified_attention_layers(cuda_device):
         assert rel(res[1][0], res[0][0]) < 1e-5, name
         for a, b in zip(res[1][1:], res[0][1:]):
             assert rel(a, b) < 1e-4, name
+
+
+# ------------------------------------------------------------------------------------------------
+# FrozenBatchNorm2d (+ identity) (+ ReLU) in one pass (step_host.fuse_frozen_bn): bitwise identical to the reference
+# ------------------------------------------------------------------------------------------------
+class FrozenBatchNorm2d(torch.nn.Module):
+    """the reference's module, restated for the test (MonoDETR/lib/models/monodetr/backbone.py:28-65)"""
+
+    def __init__(self, n, eps=1e-5):
+        super().__init__()
+        self.register_buffer("weight", torch.ones(n))
+        self.register_buffer("bias", torch.zeros(n))
+        self.register_buffer("running_mean", torch.zeros(n))
+        self.register_buffer("running_var", torch.ones(n))
+        self.eps = eps
+
+    def forward(self, x):
+        w = self.weight.reshape(1, -1, 1, 1)
+        b = self.bias.reshape(1, -1, 1, 1)
+        rv = self.running_var.reshape(1, -1, 1, 1)
+        rm = self.running_mean.reshape(1, -1, 1, 1)
+        scale = w * (rv + self.eps).rsqrt()
+        bias = b - rm * scale
+        return x * scale + bias
+
+
+def _randomise_bn(model, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, FrozenBatchNorm2d):
+            m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+            m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.3)
+            m.running_mean.copy_(torch.randn(m.bias.shape, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.bias.shape, generator=g) + 0.3)
+
+
+def test_fuse_frozen_bn_patches_and_leaves_cpu_tensors_to_the_reference_code():
+    from torchvision.models.resnet import Bottleneck
+    from monosowa_b200 import step_host
+    block = Bottleneck(16, 4, norm_layer=FrozenBatchNorm2d)
+    net = torch.nn.Sequential(block, FrozenBatchNorm2d(16))
+    _randomise_bn(net)
+    x = torch.randn(2, 16, 5, 8)
+    want = net(x)
+    assert step_host.fuse_frozen_bn(net) == 5            # bn1..bn3, the block, the trailing norm
+    assert step_host.fuse_frozen_bn(net) == 0            # idempotent
+    assert torch.equal(net(x), want)                     # CPU input: the reference's own forward runs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 64, 24, 80), (1, 16, 5, 7), (3, 32, 6, 20)], ids=lambda s: "x".join(map(str, s)))
+def test_fused_frozen_bn_is_bitwise_identical(cuda_device, shape):
+    """outputs AND gradients of: a bare FrozenBatchNorm2d; torchvision Bottleneck blocks without and with a downsample
+    branch (bn + relu twice, bn + identity + relu) -- every arithmetic step keeps the reference's rounding"""
+    import copy
+    from torchvision.models.resnet import Bottleneck
+    from monosowa_b200 import step_host
+    dev = cuda_device
+    n, c, h, w = shape
+    torch.manual_seed(11)
+    down = torch.nn.Sequential(torch.nn.Conv2d(c, c, 1, bias=False), FrozenBatchNorm2d(c))
+    ref = torch.nn.ModuleList([FrozenBatchNorm2d(c), Bottleneck(c, c // 4, norm_layer=FrozenBatchNorm2d),
+                               Bottleneck(c, c // 4, downsample=down, norm_layer=FrozenBatchNorm2d)]).to(dev)
+    _randomise_bn(ref)
+    fused = copy.deepcopy(ref)
+    assert step_host.fuse_frozen_bn(fused) == 1 + 4 + 5
+    def run(net, i, x, g):
+        net.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        y = net[i](xi)
+        y.backward(g)
+        return y.detach(), xi.grad, [p.grad.clone() for p in net[i].parameters()]
+
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+    def same(a, b, b2, what):
+        # cuDNN runs its deterministic algorithms here (flag below), so two runs of the REFERENCE agree bit for bit and
+        # so must the fused path; should a cuDNN build still not be repeatable (b vs b2), fp32 rounding noise is allowed
+        if torch.equal(b, b2):
+            assert torch.equal(a, b), f"{what} differs"
+        else:
+            assert rel(a, b) < 1e-5, f"{what} differs by {rel(a, b)}; the reference's own run-to-run noise is {rel(b2, b)}"
+
+    prev = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True               # convolution backward without run-dependent summation order
+    for i in range(3):
+        x = torch.randn(n, c, h, w, device=dev)
+        g = torch.randn(n, c, h, w, device=dev)
+        r1, r2, f = run(ref, i, x, g), run(ref, i, x, g), run(fused, i, x, g)
+        assert torch.equal(r1[0], f[0]), f"module {i}: output differs"          # forward: always bit for bit
+        same(f[1], r1[1], r2[1], f"module {i}: input gradient")
+        for a, b, b2 in zip(f[2], r1[2], r2[2]):
+            same(a, b, b2, f"module {i}: a weight gradient")
+        if i == 0:
+            assert torch.equal(f[1], r1[1]), "a bare FrozenBatchNorm2d must match bit for bit in both directions"
+    torch.backends.cudnn.deterministic = prev
+    # buffers changed (a checkpoint was loaded): the cached scale / bias must follow
+    _randomise_bn(ref, seed=5)
+    fused.load_state_dict(ref.state_dict())
+    x = torch.randn(n, c, h, w, device=dev)
+    assert torch.equal(ref[0](x), fused[0](x))

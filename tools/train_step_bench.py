@@ -179,16 +179,25 @@ def run(args):
         # (PyTorch's only fp32 fused kernel is the sm80 SIMT memory-efficient one: 24 vs ~5 ms per step, profiles/r02_training_step.md)
         want = set(args.host_opt.split(","))
         if "all" in want:
-            want |= {"matcher", "ddn", "adamw"}
+            want |= {"matcher", "ddn", "adamw", "bn"}
         with torch.no_grad():                               # same model outputs through the reference criterion ...
+            torch.manual_seed(4321)                         # (same dropout masks for the forward after the patches)
             out0 = model(images, calibs, targets, tdict["img_size"], dn_args=None)
             ld_ref = {k: float(v) for k, v in criterion(out0, targets, None, None).items()}
         host_opt = step_host.install(criterion, optimizer, matcher="matcher" in want, ddn="ddn" in want, adamw="adamw" in want,
-                                     model=model, attention="sdpa" in want)
+                                     model=model, attention="sdpa" in want, frozen_bn="bn" in want)
         with torch.no_grad():                               # ... and through the patched one: every loss term must agree
             ld_opt = {k: float(v) for k, v in criterion(out0, targets, None, None).items()}
         host_opt_check = {"loss_terms": len(ld_ref), "max_abs_diff": max(abs(ld_ref[k] - ld_opt[k]) for k in ld_ref),
                           "max_rel_diff": max(abs(ld_ref[k] - ld_opt[k]) / max(abs(ld_ref[k]), 1e-12) for k in ld_ref)}
+        if "frozen_bn" in host_opt or "sdpa" in host_opt:   # patches inside the model: its outputs before / after
+            with torch.no_grad():
+                torch.manual_seed(4321)
+                out1 = model(images, calibs, targets, tdict["img_size"], dn_args=None)
+            same = [bool(torch.equal(out0[k], out1[k])) for k in out0 if isinstance(out0[k], torch.Tensor)]
+            host_opt_check["model_outputs_bitwise_equal"] = all(same)
+            host_opt_check["model_outputs_compared"] = len(same)
+            del out1
         del out0
     img_sizes = tdict["img_size"]
     weight_dict = criterion.weight_dict
