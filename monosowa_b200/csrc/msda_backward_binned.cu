@@ -470,10 +470,11 @@ bool binned_backward_applies(const Dims &d, DType dt, bool vec_ok)
     if ((long)d.S * d.M * d.D >= (1L << 31) || d.L * d.P < 1) return false;
     if (v == 21) return true;
     // Three barrier-separated phases per CTA need several waves of CTAs to overlap each other: measured on B200
-    // (profiles/r02_kernel_family_table.jsonl) the binned kernel wins at 5120 and 6400 CTAs (KITTI batch 16, Waymo
-    // batch 4: 1.46 vs 1.53 ms, 2.06 vs 2.09 ms) and loses at ~1400 (KITTI-360 / 640x960 batch 4: 0.47 vs 0.43 ms).
+    // (profiles/r02_binned_crossover.jsonl, r02_kernel_family_table.jsonl) the binned kernel wins from ~2560 work items
+    // (KITTI batch 8: 0.75 vs 0.78 ms; batch 16: 1.43 vs 1.54; Waymo batch 4: 2.01 vs 2.09), is level around 1300-2000
+    // and loses below (KITTI batch 2: 0.26 vs 0.21 ms; KITTI-360 / 640x960 batch 4: 0.47 vs 0.43 ms).
     const long chunk = d.D <= 32 ? 256 : 128;
-    return v == -1 && d.Lq >= kBinMinQueries && (long)d.N * d.M * ((d.Lq + chunk - 1) / chunk) >= 3072;
+    return v == -1 && d.Lq >= kBinMinQueries && (long)d.N * d.M * ((d.Lq + chunk - 1) / chunk) >= 2560;
 }
 
 // grad_value (fp32) must already be zero-filled.  `ref` != nullptr selects the fused pre-processing flavour
