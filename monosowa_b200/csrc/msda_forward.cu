@@ -27,7 +27,11 @@ namespace msda {
 // FUSED: `loc` holds the raw sampling offsets, `attn` the raw attention logits and
 // `ref` the (N,Lq,L,ref_dim) reference points; locations and softmax weights are formed in registers.
 // ------------------------------------------------------------------------------------------------
-template <typename VT, int D, bool FUSED, int LOADH>
+// COMPACT: live records are packed to the front and walked with a runtime trip count (fp32: fewer loads and FMAs win);
+// !COMPACT: all G records are walked by an unrolled loop and a record outside the window is skipped by predicate
+// (bf16: the unrolled loop at <= 40 registers wins, profiles/r01_v2_compact_sweep.jsonl).  Either way a sample outside the
+// window reads nothing.
+template <typename VT, int D, bool FUSED, int LOADH, bool COMPACT = true>
 __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const float *__restrict__ loc,
                                           const float *__restrict__ attn, VT *__restrict__ out,
                                           const float *__restrict__ ref, const int ref_dim, const Dims &d,
@@ -60,6 +64,33 @@ __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const fl
         SampleIn in = fetch(gl);
         for (int b0 = 0; b0 < LP; b0 += G) {
             const int sidx = b0 + gl;
+            if constexpr (!COMPACT) {
+                int4 roff;
+                float4 rwa;
+                const SampleGeom gm = sample_geometry(valid && sidx < LP, in, s_lv, sidx / d.P, xs, roff, rwa);
+                if (!gm.live) roff.x = -1;
+                *reinterpret_cast<int4 *>(grp + gl * 4) = roff;
+                *reinterpret_cast<float4 *>(grp + RL::WEIGHTS + gl * 4) = rwa;
+                __syncwarp();
+                in = fetch(sidx + G);                                 // next batch, in flight
+#pragma unroll
+                for (int s = 0; s < G; ++s) {
+                    const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
+                    if (off.x >= 0) {
+                        const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
+                        float v00[4], v01[4], v10[4], v11[4];
+                        Vec4<VT>::template gather<LOADH>(vimg + off.x, v00);
+                        Vec4<VT>::template gather<LOADH>(vimg + off.y, v01);
+                        Vec4<VT>::template gather<LOADH>(vimg + off.z, v10);
+                        Vec4<VT>::template gather<LOADH>(vimg + off.w, v11);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
             // live records only, packed to the front of the group's area
             __align__(16) uint32_t tmp[8];
             const SampleGeom gm = build_record(tmp, tmp + 4, valid && sidx < LP, in, s_lv, sidx / d.P, xs);
@@ -94,7 +125,7 @@ __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const fl
 // record kernel: one pass, a CTA's 8 warps cover 8 * 32/G consecutive queries of one head.
 // Any L and P; D in {16, 32, 64}; fp32 or bf16 values.  Used for short query sets (the decoder).
 // ------------------------------------------------------------------------------------------------
-template <typename VT, int D, int MINB, bool FUSED = false, int LOADH = 0>
+template <typename VT, int D, int MINB, bool FUSED = false, int LOADH = 0, bool COMPACT = true>
 __global__ void __launch_bounds__(256, MINB)
 fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ lsi, const float *__restrict__ loc,
@@ -116,7 +147,7 @@ fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     if (__ballot_sync(kFullMask, w.valid) == 0) return;
     if (!w.valid) { w.n = 0; w.q = 0; w.m = 0; }
     uint32_t *grp = s_rec + (threadIdx.x >> 5) * RL::WARP_WORDS + k * RL::GROUP_WORDS;
-    fwd_group<VT, D, FUSED, LOADH>(value, loc, attn, out, ref, ref_dim, d, s_lv, grp, w.valid, w.n, w.q, w.m, gl, k);
+    fwd_group<VT, D, FUSED, LOADH, COMPACT>(value, loc, attn, out, ref, ref_dim, d, s_lv, grp, w.valid, w.n, w.q, w.m, gl, k);
 }
 
 #ifdef MSDA_AB
@@ -264,8 +295,18 @@ int run_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const fl
     // measured on B200 at configs[1] (profiles/r01_v2_compact_sweep.jsonl, r01_loadhint_sweep.jsonl): the compacting
     // loop at <= 48 registers (5 CTAs/SM); fp32 gathers with L1::no_allocate (a strip of consecutive queries has
     // little reuse, fills only compete with the gather for the data pipe), bf16 with allocating loads
-    constexpr int LOADH = sizeof(VT) == 4 ? 1 : 0;
-    fwd_rec_kernel<VT, D, 5, FUSED, LOADH><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
+    if constexpr (sizeof(VT) == 4) {
+        fwd_rec_kernel<VT, D, 5, FUSED, 1, true><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
+    } else {
+#ifdef MSDA_AB
+        if (tuning().fwd_pipe == 15) {          // A/B: the compacting loop for bf16 as well
+            fwd_rec_kernel<VT, D, 5, FUSED, 0, true><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
+            count_launch();
+            return (int)cudaGetLastError();
+        }
+#endif
+        fwd_rec_kernel<VT, D, 6, FUSED, 0, false><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
+    }
     count_launch();
     return (int)cudaGetLastError();
 }
