@@ -10,8 +10,8 @@
 //   * the bilinear geometry of a sample is computed ONCE, by one lane of the group, and shared
 //     through a 32-byte shared-memory record (msda_records.cuh) -- the first-generation kernel
 //     recomputed it in all 8 lanes and was instruction-issue bound (profiles/r01_v1_*);
-//   * samples outside the sampling window are compacted away before the gather loop (they cost
-//     neither loads nor FMAs, and -- like the reference's branch, cuh:288 -- never touch `value`);
+//   * samples outside the sampling window are skipped by predicate (they cost neither loads nor FMAs,
+//     and -- like the reference's branch, cuh:288 -- never touch `value`);
 //   * (measurement build only, -DMSDA_AB) fwd_tile_kernel: a persistent grid over 2-D image tiles (msda_tiles.cuh) --
 //     built in round 2, parity-green, slower than the record kernel (see use_tile below, profiles/r02_tile_kernels.md).
 // The op is a gather: no tensor cores; the bound is 128-byte rows through the L1 data pipe.
@@ -27,10 +27,9 @@ namespace msda {
 // FUSED: `loc` holds the raw sampling offsets, `attn` the raw attention logits and
 // `ref` the (N,Lq,L,ref_dim) reference points; locations and softmax weights are formed in registers.
 // ------------------------------------------------------------------------------------------------
-// COMPACT: live records are packed to the front and walked with a runtime trip count (fp32: fewer loads and FMAs win);
-// !COMPACT: all G records are walked by an unrolled loop and a record outside the window is skipped by predicate
-// (bf16: the unrolled loop at <= 40 registers wins, profiles/r01_v2_compact_sweep.jsonl).  Either way a sample outside the
-// window reads nothing.
+// !COMPACT (shipped): all G records of a batch are walked by an unrolled loop and a record outside the window is
+// skipped by predicate; COMPACT (measurement build): live records are packed to the front and walked with a runtime
+// trip count.  Either way a sample outside the window reads nothing.
 template <typename VT, int D, bool FUSED, int LOADH, bool COMPACT = true>
 __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const float *__restrict__ loc,
                                           const float *__restrict__ attn, VT *__restrict__ out,
@@ -292,21 +291,26 @@ int run_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const fl
     constexpr int QPW = 32 / (D / kChannelsPerLane);
     const long grid = grid_for(d, 1, QPW, 256);
     if (grid > 0x7fffffffL) return kUnsupported;
-    // measured on B200 at configs[1] (profiles/r01_v2_compact_sweep.jsonl, r01_loadhint_sweep.jsonl): the compacting
-    // loop at <= 48 registers (5 CTAs/SM); fp32 gathers with L1::no_allocate (a strip of consecutive queries has
-    // little reuse, fills only compete with the gather for the data pipe), bf16 with allocating loads
-    if constexpr (sizeof(VT) == 4) {
-        fwd_rec_kernel<VT, D, 5, FUSED, 1, true><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
-    } else {
+    // measured on B200 at configs[1], the two walks timed alternately (tools/ab_interleaved.py,
+    // profiles/r02_fwd_walks_interleaved.jsonl): the unrolled walk over all G records with outside samples skipped by
+    // predicate against the compacting loop (runtime trip count) -- bf16 0.511 vs 0.531 ms at <= 40 registers (6 CTAs/SM);
+    // fp32 a wash at <= 48 registers (5 CTAs/SM): 0.551 vs 0.557 ms with model-like locations, 0.602 vs 0.594 uniform,
+    // 0.461 vs 0.460 initial pattern (40 registers / 6 CTAs: 0.571) -- one walk for both.  fp32 gathers with L1::no_allocate (a strip of consecutive queries has little reuse, fills only
+    // compete with the gather for the data pipe: 0.59 ms with allocating loads), bf16 with allocating loads.
 #ifdef MSDA_AB
-        if (tuning().fwd_pipe == 15) {          // A/B: the compacting loop for bf16 as well
+    if (tuning().fwd_pipe == 15) {              // A/B: the compacting loop
+        if constexpr (sizeof(VT) == 4)
+            fwd_rec_kernel<VT, D, 5, FUSED, 1, true><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
+        else
             fwd_rec_kernel<VT, D, 5, FUSED, 0, true><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
-            count_launch();
-            return (int)cudaGetLastError();
-        }
-#endif
-        fwd_rec_kernel<VT, D, 6, FUSED, 0, false><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
+        count_launch();
+        return (int)cudaGetLastError();
     }
+#endif
+    if constexpr (sizeof(VT) == 4)
+        fwd_rec_kernel<VT, D, 5, FUSED, 1, false><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
+    else
+        fwd_rec_kernel<VT, D, 6, FUSED, 0, false><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
     count_launch();
     return (int)cudaGetLastError();
 }
