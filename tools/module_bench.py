@@ -35,6 +35,19 @@ def main():
     src = torch.randn(a.batch, S, 256, device=dev, requires_grad=True)
     ref = W.encoder_reference_points(W.KITTI, dev)[None].expand(a.batch, -1, -1, -1).contiguous()
     g = torch.randn(a.batch, S, 256, device=dev)
+    bench(mod, "encoder self-attention (2-dim pixel-centre references)", q, ref, src, g, sh, lsi, a)
+    # the decoder's calls: 550 training queries; layer 0 feeds learned 2-dim references WITH a gradient,
+    # layers 1-2 feed 6-dim boxes, detached (reference depthaware_transformer.py:286, 565-613)
+    qd = torch.randn(a.batch, 550, 256, device=dev, requires_grad=True)
+    gd = torch.randn(a.batch, 550, 256, device=dev)
+    ref2 = torch.rand(a.batch, 550, 1, 2, device=dev).expand(-1, -1, 4, -1).contiguous().requires_grad_(True)
+    ref6 = torch.cat([ref2.detach(), torch.rand(a.batch, 550, 4, 4, device=dev) * 0.2 + 0.02], -1)
+    bench(mod, "decoder layer 0 (550 queries, 2-dim learned references with gradient)", qd, ref2, src, gd, sh, lsi, a)
+    bench(mod, "decoder layers 1-2 (550 queries, 6-dim detached boxes)", qd, ref6, src, gd, sh, lsi, a)
+
+
+def bench(mod, call, q, ref, src, g, sh, lsi, a):
+    S = q.shape[1]
     for amp in (False, True):
         for fused in (False, True):
             mod.fuse_preprocessing = fused
@@ -47,13 +60,15 @@ def main():
                 out = fwd()
                 out.backward(g.to(out.dtype))
                 q.grad = src.grad = None
+                if ref.requires_grad:
+                    ref.grad = None
                 for p in mod.parameters():
                     p.grad = None
 
             with torch.no_grad():
                 f = timeit(fwd, a.iters)
             fb = timeit(fwd_bwd, a.iters)
-            print(json.dumps(dict(module="MSDeformAttn", tuning=a.set or "default", batch=a.batch, queries=S, autocast_bf16=amp, fused_preprocessing=fused,
+            print(json.dumps(dict(module="MSDeformAttn", call=call, tuning=a.set or "default", batch=a.batch, queries=S, autocast_bf16=amp, fused_preprocessing=fused,
                                   fwd_ms=round(f, 3), fwd_bwd_ms=round(fb, 3), peak_mem_GB=round(torch.cuda.max_memory_allocated() / 2**30, 2))),
                   flush=True)
             torch.cuda.reset_peak_memory_stats()
