@@ -34,7 +34,13 @@ namespace msda {
 // REDG.E.ADD.BF16x4 straight into the bf16 gradient -- a row receives a handful of contributions there, so the
 // per-addition rounding stays within the bf16 tolerance (tests/test_msda_gpu.py) and neither an fp32 staging
 // buffer nor a narrowing pass is needed.
-template <typename VT, int D, int MINB, bool FUSED = false, typename GVT = float>
+// CPL: channels per lane.  4: D/4 lanes per (query, head), LDG.128 gathers.  8: D/8 lanes, one 256-bit (fp32) /
+// 128-bit (bf16) gather per corner of 8 CONTIGUOUS channels -- the two record reads of a warp step then serve twice
+// as many samples.  The reductions stay 16 bytes per lane (there is no 32-byte red): chunk j of a lane covers
+// channels [j*4G + 4*gl, +4), so one REDG instruction still writes G*16 contiguous bytes of a row (whole 32-byte
+// sectors: L2 reductions are sector-bound) and the lane keeps grad_out twice: g[] for the dot
+// products (contiguous) and gr[] for the reductions (chunked).
+template <typename VT, int D, int MINB, bool FUSED = false, typename GVT = float, int CPL = kChannelsPerLane>
 __global__ void __launch_bounds__(256, MINB)
 bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ lsi, const float *__restrict__ loc,
@@ -43,11 +49,13 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                float *__restrict__ grad_attn, const Dims d, const int order,
                const float *__restrict__ ref = nullptr, const int ref_dim = 2)
 {
-    constexpr int LOADH = 0;
-    constexpr int G = D / kChannelsPerLane;
+    constexpr int LOADH = CPL == 4 ? 0 : 1;
+    constexpr int G = D / CPL;
+    constexpr int NCH = CPL / 4;                    // 16-byte reduction chunks per lane
     using RL = RecordLayout<G>;
+    using V = VecN<VT, CPL>;
     constexpr int QPW = RL::QPW;
-    static_assert(G >= 2 && G <= 32 && (32 % G) == 0, "unsupported D");
+    static_assert(G >= 2 && G <= 32 && (32 % G) == 0 && CPL % 4 == 0, "unsupported D");
 
     __shared__ LevelInfo s_lv[MSDA_MAX_LEVELS];
     __shared__ __align__(16) uint32_t s_rec[8 * RL::WARP_WORDS];
@@ -61,14 +69,26 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
 
     const int LP = d.L * d.P;
     const long qm = ((long)w.n * d.Lq + w.q) * d.M + w.m;
-    const long img = ((long)w.n * d.S * d.M + w.m) * D + gl * kChannelsPerLane;
-    const VT *vimg = value + img;
-    GVT *gvimg = grad_value + img;
+    const long img = ((long)w.n * d.S * d.M + w.m) * D;
+    const VT *vimg = value + img + gl * CPL;
+    GVT *gvimg = grad_value + img + gl * 4;
     const int xs = d.M * D;
     uint32_t *grp = s_rec + (threadIdx.x >> 5) * RL::WARP_WORDS + k * RL::GROUP_WORDS;
 
-    float g[4];
-    Vec4<VT>::load_stream(grad_out + qm * D + gl * kChannelsPerLane, g);
+    float g[CPL], gr[NCH][4];
+    V::load_stream(grad_out + qm * D + gl * CPL, g);
+    if constexpr (NCH == 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gr[0][c] = g[c];
+    } else {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) Vec4<VT>::load(grad_out + qm * D + j * 4 * G + gl * 4, gr[j]);
+    }
+    auto reduce_row = [&](int off, float wgt) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+            red_add_x4(gvimg + off + j * 4 * G, wgt * gr[j][0], wgt * gr[j][1], wgt * gr[j][2], wgt * gr[j][3]);
+    };
 
     float aw[kMaxBatches];                          // FUSED: softmax weights of this lane's samples ...
     float pa[kMaxBatches], pg[kMaxBatches];         // ... and, per processed batch, (a, d out / d a)
@@ -121,13 +141,13 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 // a sample outside the window (or past L*P) reads nothing, like the reference's branch (cuh:288, 365-367):
                 // its lanes are predicated off, so it costs no L1 wavefronts (15 % of the samples at MonoDETR's shapes)
                 if (off.x >= 0) {
-                    float v00[4], v01[4], v10[4], v11[4];
-                    Vec4<VT>::template gather<LOADH>(vimg + off.x, v00);
-                    Vec4<VT>::template gather<LOADH>(vimg + off.y, v01);
-                    Vec4<VT>::template gather<LOADH>(vimg + off.z, v10);
-                    Vec4<VT>::template gather<LOADH>(vimg + off.w, v11);
+                    float v00[CPL], v01[CPL], v10[CPL], v11[CPL];
+                    V::template gather<LOADH>(vimg + off.x, v00);
+                    V::template gather<LOADH>(vimg + off.y, v01);
+                    V::template gather<LOADH>(vimg + off.z, v10);
+                    V::template gather<LOADH>(vimg + off.w, v11);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < CPL; ++c) {
                         t[4 * u] += g[c] * v00[c];
                         t[4 * u + 1] += g[c] * v01[c];
                         t[4 * u + 2] += g[c] * v10[c];
@@ -137,10 +157,10 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 // a zero weight contributes nothing to grad_value (corner outside the map, sample outside
                 // the window, a == 0, or an exactly integral coordinate): skip the reduction -- the
                 // reduction throughput of L2 is the scarce resource of this kernel
-                if (wa.x != 0.f) red_add_x4(gvimg + off.x, wa.x * g[0], wa.x * g[1], wa.x * g[2], wa.x * g[3]);
-                if (wa.y != 0.f) red_add_x4(gvimg + off.y, wa.y * g[0], wa.y * g[1], wa.y * g[2], wa.y * g[3]);
-                if (wa.z != 0.f) red_add_x4(gvimg + off.z, wa.z * g[0], wa.z * g[1], wa.z * g[2], wa.z * g[3]);
-                if (wa.w != 0.f) red_add_x4(gvimg + off.w, wa.w * g[0], wa.w * g[1], wa.w * g[2], wa.w * g[3]);
+                if (wa.x != 0.f) reduce_row(off.x, wa.x);
+                if (wa.y != 0.f) reduce_row(off.y, wa.y);
+                if (wa.z != 0.f) reduce_row(off.z, wa.z);
+                if (wa.w != 0.f) reduce_row(off.w, wa.w);
             }
             group_reduce_scatter<G, 4 * GH>(t, gl);
             th[h][0] = t[0];
@@ -311,20 +331,44 @@ bool use_rec(const Dims &d, bool vec_ok)
            (long)d.S * d.M * d.D < (1L << 31);
 }
 
+template <typename VT, int D, bool FUSED, typename GVT, int CPL, int MINB>
+int launch_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
+               const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, int ref_dim,
+               cudaStream_t st)
+{
+    constexpr int QPW = 32 / (D / CPL);
+    const long grid = grid_for(d, 1, QPW, 256);
+    if (grid > 0x7fffffffL) return kUnsupported;
+    bwd_rec_kernel<VT, D, MINB, FUSED, GVT, CPL><<<(unsigned)grid, 256, 0, st>>>(
+        (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out, (GVT *)gv,
+        (float *)gl, (float *)ga, d, 1, (const float *)ref, ref_dim);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 template <typename VT, int D, bool FUSED, typename GVT>
 int run_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
             const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, int ref_dim,
             cudaStream_t st)
 {
-    constexpr int QPW = 32 / (D / kChannelsPerLane);
+#define MSDA_BWD_REC(CPL, MINB) \
+    launch_rec<VT, D, FUSED, GVT, CPL, MINB>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st)
+    // 8 channels per lane (profiles/r02_bwd_rec_cpl8_interleaved.jsonl, configs[1] shapes, record kernels timed
+    // alternately): D = 64 1.76 vs 2.23 ms -- 8 lanes per (query, head) like D = 32, one REDG instruction still
+    // covers whole 128-byte rows; D = 32 2.02 vs 1.54 ms -- a REDG instruction of 4-lane groups touches 8 half rows,
+    // and the reduction path charges per (instruction, row), not per byte: D = 32 keeps 4 channels per lane.
+    if constexpr (D % 8 == 0 && D / 8 >= 4) {
+        const bool ok = reinterpret_cast<uintptr_t>(value) % (8 * sizeof(VT)) == 0 &&
+                        (!FUSED || d.L * d.P <= kMaxBatches * (D / 8));
+#ifdef MSDA_AB
+        if (ok && tuning().bwd_pipe == 82) return MSDA_BWD_REC(8, 2);
+        if (ok && tuning().bwd_pipe == 83) return MSDA_BWD_REC(8, 3);
+#endif
+        if (ok && D == 64 && tuning().bwd_pipe != 4) return MSDA_BWD_REC(8, 3);
+    }
     constexpr int MINB = D <= 32 ? 3 : 1;          // 80 registers, 3 CTAs/SM (profiles/r01b_sweep_binned_flavours.jsonl)
-    const long grid = grid_for(d, 1, QPW, 256);
-    if (grid > 0x7fffffffL) return kUnsupported;
-    bwd_rec_kernel<VT, D, MINB, FUSED, GVT><<<(unsigned)grid, 256, 0, st>>>(
-        (const VT *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const VT *)grad_out, (GVT *)gv,
-        (float *)gl, (float *)ga, d, 1, (const float *)ref, ref_dim);
-    count_launch();
-    return (int)cudaGetLastError();
+    return MSDA_BWD_REC(4, MINB);
+#undef MSDA_BWD_REC
 }
 
 template <typename VT, bool FUSED, typename GVT>

@@ -30,21 +30,24 @@ namespace msda {
 // !COMPACT (shipped): all G records of a batch are walked by an unrolled loop and a record outside the window is
 // skipped by predicate; COMPACT (measurement build): live records are packed to the front and walked with a runtime
 // trip count.  Either way a sample outside the window reads nothing.
-template <typename VT, int D, bool FUSED, int LOADH, bool COMPACT = true>
+template <typename VT, int D, bool FUSED, int LOADH, bool COMPACT = true, int CPL = kChannelsPerLane>
 __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const float *__restrict__ loc,
                                           const float *__restrict__ attn, VT *__restrict__ out,
                                           const float *__restrict__ ref, const int ref_dim, const Dims &d,
                                           const LevelInfo *s_lv, uint32_t *grp, const bool valid, const int n,
                                           const int q, const int m, const int gl, const int k)
 {
-    constexpr int G = D / kChannelsPerLane;
+    constexpr int G = D / CPL;
     using RL = RecordLayout<G>;
+    using V = VecN<VT, CPL>;
     const int LP = d.L * d.P;
     const long qm = ((long)n * d.Lq + q) * d.M + m;
-    const VT *vimg = value + ((long)n * d.S * d.M + m) * D + gl * kChannelsPerLane;
+    const VT *vimg = value + ((long)n * d.S * d.M + m) * D + gl * CPL;
     const int xs = d.M * D;
 
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
     if (d.S > 0) {
         float aw[kMaxBatches];                      // FUSED: softmax weights of this lane's samples
         if constexpr (FUSED) group_softmax<G>(attn, qm * LP, LP, gl, valid, aw);
@@ -77,13 +80,13 @@ __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const fl
                     const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
                     if (off.x >= 0) {
                         const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
-                        float v00[4], v01[4], v10[4], v11[4];
-                        Vec4<VT>::template gather<LOADH>(vimg + off.x, v00);
-                        Vec4<VT>::template gather<LOADH>(vimg + off.y, v01);
-                        Vec4<VT>::template gather<LOADH>(vimg + off.z, v10);
-                        Vec4<VT>::template gather<LOADH>(vimg + off.w, v11);
+                        float v00[CPL], v01[CPL], v10[CPL], v11[CPL];
+                        V::template gather<LOADH>(vimg + off.x, v00);
+                        V::template gather<LOADH>(vimg + off.y, v01);
+                        V::template gather<LOADH>(vimg + off.z, v10);
+                        V::template gather<LOADH>(vimg + off.w, v11);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
+                        for (int c = 0; c < CPL; ++c)
                             acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
                     }
                 }
@@ -105,33 +108,33 @@ __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const fl
             for (int s = 0; s < cnt; ++s) {
                 const int4 off = *reinterpret_cast<const int4 *>(grp + s * 4);
                 const float4 wa = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
-                float v00[4], v01[4], v10[4], v11[4];
-                Vec4<VT>::template gather<LOADH>(vimg + off.x, v00);
-                Vec4<VT>::template gather<LOADH>(vimg + off.y, v01);
-                Vec4<VT>::template gather<LOADH>(vimg + off.z, v10);
-                Vec4<VT>::template gather<LOADH>(vimg + off.w, v11);
+                float v00[CPL], v01[CPL], v10[CPL], v11[CPL];
+                V::template gather<LOADH>(vimg + off.x, v00);
+                V::template gather<LOADH>(vimg + off.y, v01);
+                V::template gather<LOADH>(vimg + off.z, v10);
+                V::template gather<LOADH>(vimg + off.w, v11);
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < CPL; ++c)
                     acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
             }
             __syncwarp();
         }
     }
-    if (valid) Vec4<VT>::store(out + qm * D + gl * kChannelsPerLane, acc);
+    if (valid) V::store(out + qm * D + gl * CPL, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
 // record kernel: one pass, a CTA's 8 warps cover 8 * 32/G consecutive queries of one head.
 // Any L and P; D in {16, 32, 64}; fp32 or bf16 values.  Used for short query sets (the decoder).
 // ------------------------------------------------------------------------------------------------
-template <typename VT, int D, int MINB, bool FUSED = false, int LOADH = 0, bool COMPACT = true>
+template <typename VT, int D, int MINB, bool FUSED = false, int LOADH = 0, bool COMPACT = true, int CPL = kChannelsPerLane>
 __global__ void __launch_bounds__(256, MINB)
 fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                const int64_t *__restrict__ lsi, const float *__restrict__ loc,
                const float *__restrict__ attn, VT *__restrict__ out, const Dims d, const int order,
                const float *__restrict__ ref = nullptr, const int ref_dim = 2)
 {
-    constexpr int G = D / kChannelsPerLane;
+    constexpr int G = D / CPL;
     using RL = RecordLayout<G>;
     constexpr int QPW = RL::QPW;
     static_assert(G >= 2 && G <= 32 && (32 % G) == 0, "unsupported D");
@@ -146,7 +149,7 @@ fwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     if (__ballot_sync(kFullMask, w.valid) == 0) return;
     if (!w.valid) { w.n = 0; w.q = 0; w.m = 0; }
     uint32_t *grp = s_rec + (threadIdx.x >> 5) * RL::WARP_WORDS + k * RL::GROUP_WORDS;
-    fwd_group<VT, D, FUSED, LOADH, COMPACT>(value, loc, attn, out, ref, ref_dim, d, s_lv, grp, w.valid, w.n, w.q, w.m, gl, k);
+    fwd_group<VT, D, FUSED, LOADH, COMPACT, CPL>(value, loc, attn, out, ref, ref_dim, d, s_lv, grp, w.valid, w.n, w.q, w.m, gl, k);
 }
 
 #ifdef MSDA_AB
@@ -284,35 +287,72 @@ bool use_tile(const Dims &d)
 #endif
 }
 
+template <typename VT, int D, bool FUSED, int CPL, int MINB, int LOADH, bool COMPACT>
+int launch_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn, VT *out,
+               const Dims &d, const float *ref, int ref_dim, cudaStream_t st)
+{
+    constexpr int QPW = 32 / (D / CPL);
+    const long grid = grid_for(d, 1, QPW, 256);
+    if (grid > 0x7fffffffL) return kUnsupported;
+    fwd_rec_kernel<VT, D, MINB, FUSED, LOADH, COMPACT, CPL><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// Eight channels per lane (fp32: one 256-bit load per corner, bf16: one 128-bit load) when D allows at least four
+// lanes per (query, head): a record read costs the L1 data pipe 4 wavefronts per LDS.128 whatever the broadcast, so a
+// warp step that serves 32 / (D/8) samples instead of 32 / (D/4) halves the record share of the pipe.
+// The 256-bit load needs a 32-byte aligned base; rows are D * sizeof(VT) apart, a multiple of 32 B when D % 8 == 0.
+template <typename VT, int D, bool FUSED>
+bool wide_lanes(const VT *value, const Dims &d)
+{
+    if constexpr (D % 8 != 0 || D / 8 < 4) return false;
+    else {
+        if (tuning().fwd_pipe == 4) return false;                                  // knob: the 4-channel flavour
+        if (reinterpret_cast<uintptr_t>(value) % (8 * sizeof(VT)) != 0) return false;
+        if (FUSED && d.L * d.P > kMaxBatches * (D / 8)) return false;              // softmax batches per lane group
+        return true;
+    }
+}
+
 template <typename VT, int D, bool FUSED>
 int run_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn, VT *out,
             const Dims &d, const float *ref, int ref_dim, cudaStream_t st)
 {
-    constexpr int QPW = 32 / (D / kChannelsPerLane);
-    const long grid = grid_for(d, 1, QPW, 256);
-    if (grid > 0x7fffffffL) return kUnsupported;
-    // measured on B200 at configs[1], the two walks timed alternately (tools/ab_interleaved.py,
-    // profiles/r02_fwd_walks_interleaved.jsonl): the unrolled walk over all G records with outside samples skipped by
-    // predicate against the compacting loop (runtime trip count) -- bf16 0.511 vs 0.531 ms at <= 40 registers (6 CTAs/SM);
-    // fp32 a wash at <= 48 registers (5 CTAs/SM): 0.551 vs 0.557 ms with model-like locations, 0.602 vs 0.594 uniform,
-    // 0.461 vs 0.460 initial pattern (40 registers / 6 CTAs: 0.571) -- one walk for both.  fp32 gathers with L1::no_allocate (a strip of consecutive queries has little reuse, fills only
-    // compete with the gather for the data pipe: 0.59 ms with allocating loads), bf16 with allocating loads.
+    // measured on B200 at configs[1], the flavours timed alternately (tools/ab_interleaved.py):
+    //  * walk (profiles/r02_fwd_walks_interleaved.jsonl): the unrolled walk over all G records with outside samples
+    //    skipped by predicate against the compacting loop (runtime trip count) -- bf16 0.511 vs 0.531 ms, fp32 a wash
+    //    (0.551 vs 0.557 model-like, 0.602 vs 0.594 uniform, 0.461 vs 0.460 initial pattern) -- one walk for both;
+    //  * channels per lane (profiles/r02_fwd_cpl8_interleaved.jsonl): 8 channels per lane at <= 64 registers / 4 CTAs
+    //    per SM against 4 channels -- fp32 D=32 0.536 vs 0.562 ms (uniform 0.587 vs 0.607, initial pattern 0.445 vs
+    //    0.469; 3 CTAs the same, 5 CTAs spill: 0.65), fp32 D=64 0.495 vs 0.530, bf16 D=32 0.430 vs 0.511, bf16 D=64
+    //    0.361 vs 0.470;
+    //  * gathers with L1::no_allocate (a strip of consecutive queries has little reuse, fills only compete with the
+    //    gather for the data pipe): 8-channel fp32 0.63 ms with allocating loads, 8-channel bf16 0.439; the 4-channel
+    //    bf16 flavour (D = 16, unaligned value) keeps allocating loads as measured in round 1.
+#define MSDA_FWD_REC(CPL, MINB, LOADH, COMPACT) \
+    launch_rec<VT, D, FUSED, CPL, MINB, LOADH, COMPACT>(value, shapes, lsi, loc, attn, out, d, ref, ref_dim, st)
 #ifdef MSDA_AB
-    if (tuning().fwd_pipe == 15) {              // A/B: the compacting loop
-        if constexpr (sizeof(VT) == 4)
-            fwd_rec_kernel<VT, D, 5, FUSED, 1, true><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
-        else
-            fwd_rec_kernel<VT, D, 5, FUSED, 0, true><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
-        count_launch();
-        return (int)cudaGetLastError();
+    if (tuning().fwd_pipe == 15)                 // A/B: the compacting loop
+    {
+        if constexpr (sizeof(VT) == 4) return MSDA_FWD_REC(4, 5, 1, true);
+        else return MSDA_FWD_REC(4, 5, 0, true);
+    }
+    if constexpr (D % 8 == 0 && D / 8 >= 4) {
+        if (wide_lanes<VT, D, FUSED>(value, d)) {
+            if (tuning().fwd_pipe == 24) return MSDA_FWD_REC(8, 4, 0, false);   // A/B: allocating loads
+            if (tuning().fwd_pipe == 27) return MSDA_FWD_REC(8, 5, 1, false);   // A/B: 5 CTAs per SM (48 registers, spills)
+        }
     }
 #endif
-    if constexpr (sizeof(VT) == 4)
-        fwd_rec_kernel<VT, D, 5, FUSED, 1, false><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
-    else
-        fwd_rec_kernel<VT, D, 6, FUSED, 0, false><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
-    count_launch();
-    return (int)cudaGetLastError();
+    if constexpr (D % 8 == 0 && D / 8 >= 4) {
+        if (wide_lanes<VT, D, FUSED>(value, d)) {
+            return MSDA_FWD_REC(8, 4, 1, false);
+        }
+    }
+    if constexpr (sizeof(VT) == 4) return MSDA_FWD_REC(4, 5, 1, false);
+    else return MSDA_FWD_REC(4, 6, 0, false);
+#undef MSDA_FWD_REC
 }
 
 template <typename VT, int D, bool FUSED>

@@ -103,6 +103,90 @@ struct Vec4<__nv_bfloat16> {
     }
 };
 
+// ---- CPL-channel vectors: CPL = 4 (above) or 8 (fp32: one 256-bit LDG.E.ENL2.256, bf16: one 128-bit load)
+template <typename VT, int CPL>
+struct VecN;
+
+template <typename VT>
+struct VecN<VT, 4> {
+    template <int H>
+    static __device__ __forceinline__ void gather(const VT *p, float (&f)[4]) { Vec4<VT>::template gather<H>(p, f); }
+    static __device__ __forceinline__ void store(VT *p, const float (&f)[4]) { Vec4<VT>::store(p, f); }
+    static __device__ __forceinline__ void load(const VT *p, float (&f)[4]) { Vec4<VT>::load(p, f); }
+    static __device__ __forceinline__ void load_stream(const VT *p, float (&f)[4]) { Vec4<VT>::load_stream(p, f); }
+};
+
+template <>
+struct VecN<float, 8> {
+    template <int H>
+    static __device__ __forceinline__ void gather(const float *p, float (&f)[8])
+    {
+        if constexpr (H == 1) {
+            asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
+        } else {
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
+        }
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&f)[8])
+    {
+        __stcs(reinterpret_cast<float4 *>(p), make_float4(f[0], f[1], f[2], f[3]));
+        __stcs(reinterpret_cast<float4 *>(p) + 1, make_float4(f[4], f[5], f[6], f[7]));
+    }
+    static __device__ __forceinline__ void load(const float *p, float (&f)[8])
+    {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    static __device__ __forceinline__ void load_stream(const float *p, float (&f)[8])
+    {
+        const float4 a = __ldcs(reinterpret_cast<const float4 *>(p)), b = __ldcs(reinterpret_cast<const float4 *>(p) + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+};
+
+template <>
+struct VecN<__nv_bfloat16, 8> {
+    template <int H>
+    static __device__ __forceinline__ void gather(const __nv_bfloat16 *p, float (&f)[8])
+    {
+        uint4 v;
+        if constexpr (H == 1) {
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        } else {
+            v = __ldg(reinterpret_cast<const uint4 *>(p));
+        }
+        const unsigned u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(u[i] << 16);
+            f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&f)[8])
+    {
+        unsigned u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            u[i] = *reinterpret_cast<const unsigned *>(&h);
+        }
+        __stcs(reinterpret_cast<uint4 *>(p), make_uint4(u[0], u[1], u[2], u[3]));
+    }
+    static __device__ __forceinline__ void widen(const uint4 v, float (&f)[8])
+    {
+        const unsigned u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(u[i] << 16);
+            f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&f)[8]) { widen(__ldg(reinterpret_cast<const uint4 *>(p)), f); }
+    static __device__ __forceinline__ void load_stream(const __nv_bfloat16 *p, float (&f)[8]) { widen(__ldcs(reinterpret_cast<const uint4 *>(p)), f); }
+};
+
 // ---- per-warp record area --------------------------------------------------------------------
 // Group k (of QPW = 32/G groups) owns G records, stored as G int4 offsets followed by G float4
 // weights (so that the G lanes write 16-byte items at a 16-byte stride: conflict-free STS.128);

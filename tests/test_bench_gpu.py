@@ -12,18 +12,18 @@ pytestmark = pytest.mark.gpu
 
 
 def test_bench_line_contract(cuda_device):
-    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--sustain-steps", "3",
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "10", "--warmup", "3", "--sustain-steps", "100",
            "--cpu-steps", "1", "--no-train-step", "--no-other-configs"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [x for x in r.stdout.strip().splitlines() if x.startswith("{")]
     assert len(lines) == 1, "exactly one JSON line on stdout"
     d = json.loads(lines[0])
-    assert d["metric"] == "MSDA fwd+bwd GB/s" and d["unit"] == "GB/s" and d["n_gpus"] == 1 and d["steps"] == 3
+    assert d["metric"] == "MSDA fwd+bwd GB/s" and d["unit"] == "GB/s" and d["n_gpus"] == 1 and d["steps"] == 10
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f32"
     assert d["config"]["workload"].startswith("BASELINE.json configs[1]") and d["data"] == "synthetic"
-    assert d["value"] > 300 and abs(d["value"] - d["value_sustained"]) / d["value"] < 0.2
-    assert d["gpu_launches"] == 6, "3 timed steps = 3 forward + 3 backward launches of libmsda_b200.so"
+    assert d["value"] > 300 and abs(d["value"] - d["value_sustained"]) / d["value"] < 0.25, (d["value"], d["value_sustained"])
+    assert d["gpu_launches"] == 20, "10 timed steps = 10 forward + 10 backward launches of libmsda_b200.so"
     assert d["kernels"] == {"fwd": "fwd_rec_f32", "bwd": "bwd_bin_f32"}
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["kernel"] == "bwd" and rf["unit"] == "GB/s" and rf["traffic"] > 0

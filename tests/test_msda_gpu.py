@@ -244,6 +244,47 @@ def test_generic_and_record_kernels_agree(msda):
         assert O.rel_l2(x, y) < tol
 
 
+@pytest.mark.parametrize("D", [32, 64])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_forward_lane_widths_agree_bitwise(msda, cuda_device, D, dtype):
+    """the forward gathers 8 channels per lane (one 256-bit / 128-bit load) when D >= 32 and `value` is aligned to
+    8 elements, 4 channels per lane otherwise (fwd_pipe = 4 forces it): same samples in the same order per channel,
+    so the outputs are bit-identical -- checked through the knob and through a `value` view that is 16- but not
+    32-byte aligned."""
+    value, sh, lsi, loc, attn, _ = _random_case(21, [(12, 40), (6, 20), (3, 10), (2, 5)], 2, 4, D, 333, 4, spread=1.4, shift=-0.2)
+    dev = cuda_device
+    v = value.to(dtype).to(dev)
+    args = (sh.to(dev), lsi.to(dev), loc.float().to(dev), attn.float().to(dev))
+    wide = torch.ops.msda.forward(v, *args, 64)
+    ref = O.forward_c(v.double().cpu(), sh, lsi, loc.float().double(), attn.float().double())
+    assert O.rel_l2(wide, ref) < TOL[dtype]["fwd"]
+    msda._lib.set_tuning("fwd_pipe", 4)
+    try:
+        narrow = torch.ops.msda.forward(v, *args, 64)
+    finally:
+        msda._lib.set_tuning("fwd_pipe", -1)
+    assert torch.equal(wide, narrow)
+    shift = 16 // v.element_size()                       # elements in 16 bytes
+    flat = torch.empty(v.numel() + shift, dtype=dtype, device=dev)
+    off = shift if flat.data_ptr() % 32 == 0 else 0
+    view = flat[off:off + v.numel()].view_as(v)
+    view.copy_(v)
+    assert view.data_ptr() % 32 == 16
+    assert torch.equal(torch.ops.msda.forward(view, *args, 64), wide)
+    # the record backward takes 8 channels per lane for D = 64 only (bwd_pipe = 4 forces 4): the per-lane partial
+    # dot products are summed in a different order, so agreement is to rounding
+    g = torch.randn_like(wide)
+    b_wide = torch.ops.msda.backward(v, *args, g, 64)
+    msda._lib.set_tuning("bwd_pipe", 4)
+    try:
+        b_narrow = torch.ops.msda.backward(v, *args, g, 64)
+    finally:
+        msda._lib.set_tuning("bwd_pipe", -1)
+    b_view = torch.ops.msda.backward(view, *args, g, 64)
+    for x, y, z, tol in zip(b_wide, b_narrow, b_view, (1e-2 if dtype == torch.bfloat16 else 1e-5, 1e-5, 1e-5)):
+        assert O.rel_l2(x, y) < tol and O.rel_l2(z, y) < tol
+
+
 # --- binned backward (msda_backward_binned.cu; the default for long query sets) and the tile kernels (msda_tiles.cuh,
 # fwd_tile_kernel, msda_backward_tiled.cu; measurement build only) ---------------------------------------------------
 # binned: chunks of 256 consecutive queries of one head; the grad_value contributions of the COARSE levels (decided on

@@ -20,9 +20,11 @@ ap.add_argument("--dtype", default="f32")
 ap.add_argument("--mode", default="model")
 ap.add_argument("--rounds", type=int, default=6)
 ap.add_argument("--what", default="fwd", choices=["fwd", "bwd"])
+ap.add_argument("--head-dim", type=int, default=32)
+ap.add_argument("--heads", type=int, default=8)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
-wl = W.config(1, loc_mode=args.mode, dtype={"f32": torch.float32, "bf16": torch.bfloat16}[args.dtype])
+wl = W.config(1, loc_mode=args.mode, head_dim=args.head_dim, heads=args.heads, dtype={"f32": torch.float32, "bf16": torch.bfloat16}[args.dtype])
 d = W.make_inputs(wl, device=dev)
 a5 = (d["value"], d["shapes"], d["lsi"], d["loc"], d["attn"])
 fn = (lambda: torch.ops.msda.forward(*a5, 64)) if args.what == "fwd" else (lambda: torch.ops.msda.backward(*a5, d["grad_out"], 64))
@@ -41,6 +43,6 @@ for r in range(args.rounds):
     for cfg in ((args.a, args.b) if r % 2 == 0 else (args.b, args.a)):
         apply(cfg)
         res[cfg].append(timeit(fn, 30))
-print(json.dumps({"what": args.what, "dtype": args.dtype, "mode": args.mode,
+print(json.dumps({"what": args.what, "dtype": args.dtype, "mode": args.mode, "head_dim": args.head_dim, "heads": args.heads,
                   **{k: {"median_ms": round(statistics.median(v), 4), "min_ms": round(min(v), 4), "all": [round(x, 4) for x in v]}
                      for k, v in res.items()}}))
