@@ -30,7 +30,7 @@ namespace msda {
 // !COMPACT (shipped): all G records of a batch are walked by an unrolled loop and a record outside the window is
 // skipped by predicate; COMPACT (measurement build): live records are packed to the front and walked with a runtime
 // trip count.  Either way a sample outside the window reads nothing.
-template <typename VT, int D, bool FUSED, int LOADH, bool COMPACT = true, int CPL = kChannelsPerLane>
+template <typename VT, int D, bool FUSED, int LOADH_, bool COMPACT = true, int CPL = kChannelsPerLane>
 __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const float *__restrict__ loc,
                                           const float *__restrict__ attn, VT *__restrict__ out,
                                           const float *__restrict__ ref, const int ref_dim, const Dims &d,
@@ -40,6 +40,9 @@ __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const fl
     constexpr int G = D / CPL;
     using RL = RecordLayout<G>;
     using V = VecN<VT, CPL>;
+    // LOADH_ = gather policy (Vec4 / VecN::gather) + 16 * stream-policy override (0: by lane-group size, see
+    // ld_stream2 in msda_records.cuh; k > 0 forces policy k - 1)
+    constexpr int LOADH = LOADH_ % 16, SP = (LOADH_ / 16) ? LOADH_ / 16 - 1 : stream_policy<G>();
     const int LP = d.L * d.P;
     const long qm = ((long)n * d.Lq + q) * d.M + m;
     const VT *vimg = value + ((long)n * d.S * d.M + m) * D + gl * CPL;
@@ -55,12 +58,12 @@ __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const fl
             const bool has = valid && sidx < LP;
             if constexpr (FUSED) {
                 const int l = has ? sidx / d.P : 0;
-                const SampleIn r = fetch_sample_fused(has, loc, ref, ref_dim, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv,
-                                                      l, d.P, aw[0]);
+                const SampleIn r = fetch_sample_fused<SP>(has, loc, ref, ref_dim, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv,
+                                                          l, d.P, aw[0]);
                 aw[0] = aw[1]; aw[1] = aw[2]; aw[2] = aw[3];          // aw[0] = weight of the next batch
                 return r;
             } else {
-                return fetch_sample(has, loc, attn, qm * LP + sidx);
+                return fetch_sample<SP>(has, loc, attn, qm * LP + sidx);
             }
         };
         SampleIn in = fetch(gl);
@@ -341,6 +344,11 @@ int run_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const fl
     if constexpr (D % 8 == 0 && D / 8 >= 4) {
         if (wide_lanes<VT, D, FUSED>(value, d)) {
             if (tuning().fwd_pipe == 24) return MSDA_FWD_REC(8, 4, 0, false);   // A/B: allocating loads
+            if constexpr (sizeof(VT) == 4) {
+                if (tuning().fwd_pipe == 30) return MSDA_FWD_REC(8, 4, 3, false);        // A/B: L2::evict_last on the gathers
+            }
+            if (tuning().fwd_pipe == 31) return MSDA_FWD_REC(8, 4, 16 + 1, false);       // A/B: evict-first streams
+            if (tuning().fwd_pipe == 33) return MSDA_FWD_REC(8, 4, 48 + 1, false);       // A/B: evict-first streams, L2::128B hint
             if (tuning().fwd_pipe == 27) return MSDA_FWD_REC(8, 5, 1, false);   // A/B: 5 CTAs per SM (48 registers, spills)
         }
     }

@@ -124,6 +124,9 @@ struct VecN<float, 8> {
         if constexpr (H == 1) {
             asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
+        } else if constexpr (H == 3) {     // as 1, and the row is the last to leave L2
+            asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
         } else {
             asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
@@ -189,9 +192,13 @@ struct VecN<__nv_bfloat16, 8> {
 
 // ---- per-warp record area --------------------------------------------------------------------
 // Group k (of QPW = 32/G groups) owns G records, stored as G int4 offsets followed by G float4
-// weights (so that the G lanes write 16-byte items at a 16-byte stride: conflict-free STS.128);
-// groups are 4 words apart modulo the 32 banks so that the broadcast reads of the QPW groups
-// never collide.
+// weights (so that the G lanes write 16-byte items at a 16-byte stride).  Groups are 4 words apart
+// modulo the 32 banks so that the broadcast READS of the QPW groups (same record index, one address
+// per group) never collide -- there are 2*G reads for every 2 writes.  For G < 8 the record WRITES of
+// neighbouring groups then overlap in 3 of 4 bank quads (ncu, 4-lane forward: 6.2 M of 24.3 M shared
+// wavefronts); the alternative stride 4*G (conflict-free writes, 4-way read conflicts: 10.7 M of 28.8 M)
+// was measured no faster (profiles/r02_fwd_layout_interleaved.jsonl) and a stride that serves both does
+// not exist without a per-record swizzle (reads need stride/4 odd, writes need stride = 16 mod 32).
 template <int G>
 struct RecordLayout {
     static constexpr int QPW = 32 / G;
@@ -218,15 +225,48 @@ struct SampleIn {
     float ex, ey;               // fused 6-dim reference points only: (l+r, t+b) of the reference box
 };
 
+// Loads of the read-once input streams (locations / offsets, weights).  A lane group reads the G samples of a batch,
+// i.e. G*8 bytes of its (query, head)'s location line per batch, the batches microseconds apart.
+// SP = 0: ld.global.cs (evict-first: keeps the streams from displacing the value lines the gather re-uses) -- for
+//   G >= 8, where a batch asks for 64 bytes, what DRAM delivers.
+// SP = 1: ld.global.nc (evict-normal) -- for G < 8: a batch asks for one 32-byte sector, and the evict-first half of
+//   the 64-byte DRAM burst that is not asked for yet is gone again when its batch comes (ncu, 8-channel fp32 forward at
+//   configs[1]: 572 MB of DRAM reads with SP = 0, 418 MB = the compulsory inputs with SP = 1, same run time;
+//   profiles/r02_fwd_dram_by_flavour.txt).
+// SP = 2: evict-first with an L2::128B prefetch hint (A/B: does not keep the line either, 574 MB).
+template <int G>
+__host__ __device__ constexpr int stream_policy() { return G < 8 ? 1 : 0; }
+
+template <int SP>
+__device__ __forceinline__ float2 ld_stream2(const float2 *p)
+{
+    if constexpr (SP == 1) return __ldg(p);
+    else if constexpr (SP == 2) {
+        float2 v;
+        asm volatile("ld.global.cs.L2::128B.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+        return v;
+    } else return __ldcs(p);
+}
+template <int SP>
+__device__ __forceinline__ float ld_stream1(const float *p)
+{
+    if constexpr (SP == 1) return __ldg(p);
+    else if constexpr (SP == 2) {
+        float v;
+        asm volatile("ld.global.cs.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+        return v;
+    } else return __ldcs(p);
+}
+
+template <int SP = 0>
 __device__ __forceinline__ SampleIn fetch_sample(bool has, const float *__restrict__ loc,
                                                  const float *__restrict__ attn, long sample_index)
 {
     SampleIn in{0.f, 0.f, 0.f, 0.f, 0.f};
     if (has) {
-        // read-once streams: keep them from displacing the value lines that the gather re-uses in L1/L2
-        const float2 xy = __ldcs(reinterpret_cast<const float2 *>(loc) + sample_index);
+        const float2 xy = ld_stream2<SP>(reinterpret_cast<const float2 *>(loc) + sample_index);
         in.x = xy.x; in.y = xy.y;
-        in.a = __ldcs(attn + sample_index);
+        in.a = ld_stream1<SP>(attn + sample_index);
     }
     return in;
 }
@@ -286,13 +326,14 @@ __device__ __forceinline__ void group_softmax(const float *__restrict__ logits, 
 //   ref_dim 2:  loc = ref + off / (W, H)
 //   ref_dim 6:  loc = ref[:2] + ((off / P) * (ref[2]+ref[3], ref[4]+ref[5])) * 0.5
 // the attention weight comes from group_softmax
+template <int SP = 0>
 __device__ __forceinline__ SampleIn fetch_sample_fused(bool has, const float *__restrict__ offsets,
                                                        const float *__restrict__ ref, int ref_dim, long sample_index,
                                                        long ref_index, const LevelInfo *s_lv, int l, int P, float a)
 {
     SampleIn in{0.f, 0.f, 0.f, 0.f, 0.f};
     if (has) {
-        const float2 o = __ldcs(reinterpret_cast<const float2 *>(offsets) + sample_index);
+        const float2 o = ld_stream2<SP>(reinterpret_cast<const float2 *>(offsets) + sample_index);
         if (ref_dim == 2) {
             const float2 r = __ldg(reinterpret_cast<const float2 *>(ref) + ref_index);
             const LevelInfo li = s_lv[l];

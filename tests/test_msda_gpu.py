@@ -349,10 +349,11 @@ def _tile_vs_oracle_and_record(msda, case_inputs, dtype, label, variants=(12, 20
         L.set_tuning("fwd_variant", variants[0]); L.set_tuning("bwd_variant", variants[1])
         check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=label)
         b = run_ours(msda, value.to(dtype), sh, lsi, loc.to(ct), attn.to(ct), grad_out.to(dtype))
-        L.set_tuning("fwd_variant", 11); L.set_tuning("bwd_variant", 11)
+        # the 4-channel-per-lane record backward: the same partial sums in the same order as the binned / tile kernels
+        L.set_tuning("fwd_variant", 11); L.set_tuning("bwd_variant", 11); L.set_tuning("bwd_pipe", 4)
         a = run_ours(msda, value.to(dtype), sh, lsi, loc.to(ct), attn.to(ct), grad_out.to(dtype))
     finally:
-        L.set_tuning("fwd_variant", -1); L.set_tuning("bwd_variant", -1)
+        L.set_tuning("fwd_variant", -1); L.set_tuning("bwd_variant", -1); L.set_tuning("bwd_pipe", -1)
     assert torch.equal(a[0], b[0]), "forward differs from the record kernel"
     assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]), "grad_loc / grad_attn differ from the record kernel"
     assert O.rel_l2(b[1], a[1]) < (1e-5 if dtype == torch.float32 else 1e-2)
@@ -829,6 +830,8 @@ FUSED_CASES = [
     ([(9, 7), (5, 4)], 3, 3, 16, 17, 2),                      # 4-lane groups, one batch
     ([(9, 7), (5, 4), (3, 3), (2, 2)], 1, 2, 64, 9, 4),       # 16-lane groups
     ([(9, 7), (5, 4), (3, 3), (2, 2)], 1, 2, 16, 9, 4),       # L*P = 16 = 4 batches of 4 lanes
+    ([(9, 7), (5, 4), (3, 3)], 1, 2, 32, 9, 8),               # L*P = 24 > 4 batches of the 4-lane (8-channel) groups: 8-lane flavour
+    ([(9, 7), (5, 4), (3, 3), (2, 2), (1, 1)], 1, 2, 64, 9, 8),   # L*P = 40: D = 64 falls back to 16-lane groups
 ]
 
 
