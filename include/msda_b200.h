@@ -185,7 +185,8 @@ long long msda_launch_count(void);     /* kernels this library has launched so f
  * against concurrent launches).  Keys: "fwd_variant" (11 = record kernel, 99 = generic kernel;
  * 12 = tile kernel, -DMSDA_AB builds only), "bwd_variant" (11 = record kernel for any Lq, 21 = binned
  * kernel for any Lq, 99 = generic kernel; 20 = tile kernel, -DMSDA_AB builds only), "fwd_pipe" /
- * "bwd_pipe" (launch flavours of the -DMSDA_AB kernels; ignored by the shipped library).  value -1 restores the default.
+ * "bwd_pipe" (4 = four channels per lane in the record kernels, where the default would take eight; other values:
+ * launch flavours of the -DMSDA_AB kernels, ignored by the shipped library).  value -1 restores the default.
  * Returns MSDA_OK or MSDA_ERR_BAD_SHAPE (unknown key). */
 int msda_set_tuning(const char *key, int value);
 int msda_get_tuning(const char *key);
