@@ -35,6 +35,11 @@
  * Semantics: pixel coordinate = loc * size - 0.5 (grid_sample align_corners=False), bilinear,
  * zero padding per corner, samples outside (-1, size) skipped (cuh:285-291, 33-84).
  *
+ * Alignment: every pointer must be aligned to its element size (else MSDA_ERR_MISALIGNED).  The fast kernels
+ * (D in {16, 32, 64}) need 16-byte aligned tensor pointers, and the forward takes its widest loads (eight channels
+ * per lane) when `value` is aligned to eight elements (32 bytes fp32, 16 bytes bf16); anything less aligned runs the
+ * narrower or the generic kernels with identical results -- torch allocations are 512-byte aligned.
+ *
  * Every entry point enqueues work on `stream` (a cudaStream_t passed as void*; NULL = the
  * legacy default stream) and returns immediately: no host synchronisation, no host reads of
  * device metadata, safe inside CUDA-graph capture.  Return value: MSDA_OK, a negative
