@@ -652,7 +652,7 @@ def main():
     ap.add_argument("--loc-mode", default="model", choices=["model", "uniform"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--e2e-chunks", type=int, default=8)
-    ap.add_argument("--e2e-images-per-chunk", type=int, default=1)
+    ap.add_argument("--e2e-images-per-chunk", type=int, default=2)
     ap.add_argument("--e2e-stages", type=int, default=3, help="device stages of the host-step pipeline (3..16)")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")

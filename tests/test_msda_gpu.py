@@ -752,7 +752,7 @@ def _guard_bands(msda, cuda_device, dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("per_chunk", [1, 2, 5])
+@pytest.mark.parametrize("per_chunk", [1, 2, 3, 5])
 def test_host_buffer_step_matches_device_path(msda, cuda_device, dtype, per_chunk):
     """msda_host_step_*: pinned host tensors in, pinned host results out, pipelined over the batch (7 images:
     more chunks than pipeline stages, a ragged last chunk).  Same kernels as the device path: out, grad_loc and
