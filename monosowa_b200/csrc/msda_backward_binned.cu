@@ -38,12 +38,15 @@ constexpr int kBinThreads = 256;
 constexpr unsigned kNoEntry = 0xffffffffu;
 constexpr int kBinMinQueries = 1024;  // below this the chunks are too few / too short to pay for the two extra phases
 
-template <int D, int QCQ = 0>
+// CPL: channels per lane -- 4, or 8 for D = 64 (8 lanes per (query, head) like D = 32: see bwd_rec_kernel for the lane /
+// reduction-chunk layout and why D = 32 stays at 4)
+template <int D, int QCQ = 0, int CPL = kChannelsPerLane>
 struct BinCfg {
-    static constexpr int G = D / kChannelsPerLane;
+    static constexpr int G = D / CPL;
+    static constexpr int NCH = CPL / 4;                           // 16-byte reduction chunks per lane
     static constexpr int QPW = 32 / G;
     static constexpr int QPI = (kBinThreads / 32) * QPW;          // queries per pass of the CTA's warps
-    static constexpr int QC = QCQ > 0 ? QCQ : (D <= 32 ? 256 : 128);   // queries per CTA
+    static constexpr int QC = QCQ > 0 ? QCQ : (G <= 8 ? 256 : 128);    // queries per CTA
     static constexpr int HIST_HALVES = kMaxBins + 2;              // 16-bit counters, packed two per word
     static constexpr int HIST_WORDS = (HIST_HALVES + 1) / 2;
     static constexpr int G_BYTES = 0;                             // the chunk's grad_out rows are re-read from L1/L2
@@ -64,22 +67,21 @@ struct BinPlan {
     int binbase[MSDA_MAX_LEVELS];    // first cell of each binned level
 };
 
-template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3>
+template <typename VT, int D, bool FUSED, int QCQ = 0, int MINB = 3, int CPL = kChannelsPerLane>
 __global__ void __launch_bounds__(kBinThreads, MINB)
 bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ loc, const float *__restrict__ attn, const VT *__restrict__ grad_out,
                float *__restrict__ grad_value, float *__restrict__ grad_loc, float *__restrict__ grad_attn,
                const Dims d, const float *__restrict__ ref, const int ref_dim, const int max_binned)
 {
-    constexpr bool GS = false;
-    constexpr int LDQ = 1, LOADH = 0, RUN = 4;
-    using C = BinCfg<D, QCQ>;
+    constexpr int LDQ = 1, LOADH = CPL == 4 ? 0 : 1, RUN = 4;
+    using C = BinCfg<D, QCQ, CPL>;
     using RL = RecordLayout<C::G>;
-    constexpr int G = C::G, QPW = C::QPW, QPI = C::QPI, QC = C::QC;
+    using V = VecN<VT, CPL>;
+    constexpr int G = C::G, QPW = C::QPW, QPI = C::QPI, QC = C::QC, NCH = C::NCH;
     constexpr int LD = (LDQ <= G / 2) ? LDQ : G / 2;     // samples whose loads are issued together
 
     extern __shared__ __align__(16) unsigned char smem[];
-    float *s_g = reinterpret_cast<float *>(smem);
     uint4 *s_ent = reinterpret_cast<uint4 *>(smem + C::G_BYTES);
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + C::G_BYTES + C::ENT_BYTES);
     uint32_t *s_rec = reinterpret_cast<uint32_t *>(smem + C::G_BYTES + C::ENT_BYTES + C::HIST_BYTES);
@@ -122,9 +124,9 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
 
     const int LP = d.L * d.P;
     const int lbP = s_plan.lbP;
-    const long img = ((long)n * d.S * d.M + m) * D + gl * kChannelsPerLane;
-    const VT *vimg = value + img;
-    float *gvimg = grad_value + img;
+    const long img = ((long)n * d.S * d.M + m) * D;
+    const VT *vimg = value + img + gl * CPL;             // gathers: CPL contiguous channels
+    float *gvimg = grad_value + img + gl * 4;            // reductions: chunk j = channels [j*4G + 4*gl, +4)
     const int xs = d.M * D;
     uint32_t *grp = s_rec + warp * RL::WARP_WORDS + k * RL::GROUP_WORDS;
 
@@ -136,13 +138,20 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
         const bool qvalid = q0 + ql < d.Lq;
         const long qm = ((long)n * d.Lq + (qvalid ? q0 + ql : q0)) * d.M + m;
 
-        float g[4];
-        if constexpr (GS) {
-            Vec4<VT>::load_stream(grad_out + qm * D + gl * kChannelsPerLane, g);
-            *reinterpret_cast<float4 *>(s_g + ql * D + gl * kChannelsPerLane) = make_float4(g[0], g[1], g[2], g[3]);
+        float g[CPL], gr[NCH][4];
+        V::load(grad_out + qm * D + gl * CPL, g);                              // read again by phase C: keep it cached
+        if constexpr (NCH == 1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gr[0][c] = g[c];
         } else {
-            Vec4<VT>::load(grad_out + qm * D + gl * kChannelsPerLane, g);      // read again by phase C: keep it cached
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) Vec4<VT>::load(grad_out + qm * D + j * 4 * G + gl * 4, gr[j]);
         }
+        auto reduce_row = [&](int off, float wgt) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+                red_add_f32x4(gvimg + off + j * 4 * G, wgt * gr[j][0], wgt * gr[j][1], wgt * gr[j][2], wgt * gr[j][3]);
+        };
 
         float aw[kMaxBatches];
         float pa[kMaxBatches], pg[kMaxBatches];
@@ -204,22 +213,20 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 for (int u0 = 0; u0 < GH; u0 += LD) {
                     int4 off[LD];
                     float4 wa[LD];
-                    float v[LD][4][4];
+                    float v[LD][4][CPL];
 #pragma unroll
                     for (int j = 0; j < LD; ++j) {
                         const int s = h * GH + u0 + j;
                         off[j] = *reinterpret_cast<const int4 *>(grp + s * 4);
                         wa[j] = *reinterpret_cast<const float4 *>(grp + RL::WEIGHTS + s * 4);
-                        v[j][0][0] = v[j][0][1] = v[j][0][2] = v[j][0][3] = 0.f;
-                        v[j][1][0] = v[j][1][1] = v[j][1][2] = v[j][1][3] = 0.f;
-                        v[j][2][0] = v[j][2][1] = v[j][2][2] = v[j][2][3] = 0.f;
-                        v[j][3][0] = v[j][3][1] = v[j][3][2] = v[j][3][3] = 0.f;
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) v[j][0][c] = v[j][1][c] = v[j][2][c] = v[j][3][c] = 0.f;
                         // outside the window / past L*P: nothing is read (the reference's branch, cuh:288, 365-367)
                         if (off[j].x >= 0) {
-                            Vec4<VT>::template gather<LOADH>(vimg + off[j].x, v[j][0]);
-                            Vec4<VT>::template gather<LOADH>(vimg + off[j].y, v[j][1]);
-                            Vec4<VT>::template gather<LOADH>(vimg + off[j].z, v[j][2]);
-                            Vec4<VT>::template gather<LOADH>(vimg + off[j].w, v[j][3]);
+                            V::template gather<LOADH>(vimg + off[j].x, v[j][0]);
+                            V::template gather<LOADH>(vimg + off[j].y, v[j][1]);
+                            V::template gather<LOADH>(vimg + off[j].z, v[j][2]);
+                            V::template gather<LOADH>(vimg + off[j].w, v[j][3]);
                         }
                     }
 #pragma unroll
@@ -228,7 +235,7 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                         t[4 * u] = t[4 * u + 1] = t[4 * u + 2] = t[4 * u + 3] = 0.f;
                         if (d.S > 0) {
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
+                            for (int c = 0; c < CPL; ++c) {
                                 t[4 * u] += g[c] * v[j][0][c];
                                 t[4 * u + 1] += g[c] * v[j][1][c];
                                 t[4 * u + 2] += g[c] * v[j][2][c];
@@ -236,10 +243,10 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                             }
                         }
                         if (b0 + s < lbP) {                  // fine level (warp-uniform): direct reductions
-                            if (wa[j].x != 0.f) red_add_f32x4(gvimg + off[j].x, wa[j].x * g[0], wa[j].x * g[1], wa[j].x * g[2], wa[j].x * g[3]);
-                            if (wa[j].y != 0.f) red_add_f32x4(gvimg + off[j].y, wa[j].y * g[0], wa[j].y * g[1], wa[j].y * g[2], wa[j].y * g[3]);
-                            if (wa[j].z != 0.f) red_add_f32x4(gvimg + off[j].z, wa[j].z * g[0], wa[j].z * g[1], wa[j].z * g[2], wa[j].z * g[3]);
-                            if (wa[j].w != 0.f) red_add_f32x4(gvimg + off[j].w, wa[j].w * g[0], wa[j].w * g[1], wa[j].w * g[2], wa[j].w * g[3]);
+                            if (wa[j].x != 0.f) reduce_row(off[j].x, wa[j].x);
+                            if (wa[j].y != 0.f) reduce_row(off[j].y, wa[j].y);
+                            if (wa[j].z != 0.f) reduce_row(off[j].z, wa[j].z);
+                            if (wa[j].w != 0.f) reduce_row(off[j].w, wa[j].w);
                         }
                     }
                 }
@@ -352,16 +359,23 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
     // noise, profiles/r01b_sweep_cell_runs.jsonl -- the flush is not what paces the kernel).
     const unsigned gmask = (G == 32) ? kFullMask : (((1u << G) - 1u) << (lane & ~(G - 1)));
     const int nbins = s_plan.nbins, lb = s_plan.lb;
-    const float *gq = s_g + gl * kChannelsPerLane;
-    const VT *gq_global = grad_out + (((long)n * d.Lq + q0) * d.M + m) * D + gl * kChannelsPerLane;
+    const VT *gq_global = grad_out + (((long)n * d.Lq + q0) * d.M + m) * D + gl * 4;
+    auto flush = [&](float *p, const float (&acc)[NCH][4]) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) red_add_f32x4(p + j * 4 * G, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+    };
     for (;;) {
         int c0 = 0;
         if (gl == 0) c0 = atomicAdd(&s_next, RUN);
         c0 = __shfl_sync(gmask, c0, 0, G);
         if (c0 >= nbins) break;
         const int c1 = min(c0 + RUN, nbins);
-        float l0[4] = {0.f, 0.f, 0.f, 0.f}, l1[4] = {0.f, 0.f, 0.f, 0.f};      // corners (y0, x0), (y1, x0)
-        float r0[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f};      // corners (y0, x1), (y1, x1)
+        float l0[NCH][4], l1[NCH][4];                                          // corners (y0, x0), (y1, x0)
+        float r0[NCH][4], r1[NCH][4];                                          // corners (y0, x1), (y1, x1)
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) l0[j][k2] = l1[j][k2] = r0[j][k2] = r1[j][k2] = 0.f;
         bool lt = false, rt = false;                                           // accumulators hold something
         for (int c = c0; c < c1; ++c) {
             int l = lb;
@@ -374,21 +388,21 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
             for (int i = i0; i < i1; ++i) {
                 const int e = s_idx[i];
                 const uint4 en = s_ent[e];
-                float4 gg;
-                if constexpr (GS) {
-                    gg = *reinterpret_cast<const float4 *>(gq + (e / kBinSamples) * D);
-                } else {
-                    float gt[4];
-                    Vec4<VT>::load(gq_global + (long)(e / kBinSamples) * xs, gt);
-                    gg = make_float4(gt[0], gt[1], gt[2], gt[3]);
-                }
                 const float a = __uint_as_float(en.x), lx = __uint_as_float(en.y), ly = __uint_as_float(en.z);
                 const float hy = 1.f - ly, hx = 1.f - lx;
                 const float w00 = (hy * hx) * a, w01 = (hy * lx) * a, w10 = (ly * hx) * a, w11 = (ly * lx) * a;
-                l0[0] += w00 * gg.x; l0[1] += w00 * gg.y; l0[2] += w00 * gg.z; l0[3] += w00 * gg.w;
-                r0[0] += w01 * gg.x; r0[1] += w01 * gg.y; r0[2] += w01 * gg.z; r0[3] += w01 * gg.w;
-                l1[0] += w10 * gg.x; l1[1] += w10 * gg.y; l1[2] += w10 * gg.z; l1[3] += w10 * gg.w;
-                r1[0] += w11 * gg.x; r1[1] += w11 * gg.y; r1[2] += w11 * gg.z; r1[3] += w11 * gg.w;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    float gt[4];
+                    Vec4<VT>::load(gq_global + (long)(e / kBinSamples) * xs + j * 4 * G, gt);
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) {
+                        l0[j][k2] += w00 * gt[k2];
+                        r0[j][k2] += w01 * gt[k2];
+                        l1[j][k2] += w10 * gt[k2];
+                        r1[j][k2] += w11 * gt[k2];
+                    }
+                }
             }
             if (i1 > i0) lt = rt = true;
             // corners outside the map receive nothing (zero padding, ms_deform_im2col_cuda.cuh:125-152)
@@ -397,37 +411,37 @@ bwd_bin_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
             float *row = gvimg + (li.start + y0 * li.W + x0) * xs;             // pixel (y0, x0)
             const int ys = li.W * xs;
             if (lt && x0 >= 0) {                                               // the left column is complete now
-                if (y0ok) red_add_f32x4(row, l0[0], l0[1], l0[2], l0[3]);
-                if (y1ok) red_add_f32x4(row + ys, l1[0], l1[1], l1[2], l1[3]);
+                if (y0ok) flush(row, l0);
+                if (y1ok) flush(row + ys, l1);
             }
             if (c + 1 < c1 && bx < li.W) {                                     // next cell continues this lattice row
 #pragma unroll
-                for (int k2 = 0; k2 < 4; ++k2) { l0[k2] = r0[k2]; l1[k2] = r1[k2]; r0[k2] = 0.f; r1[k2] = 0.f; }
+                for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) { l0[j][k2] = r0[j][k2]; l1[j][k2] = r1[j][k2]; r0[j][k2] = 0.f; r1[j][k2] = 0.f; }
                 lt = rt;
                 rt = false;
             } else {
                 if (rt && bx <= li.W - 1) {
-                    if (y0ok) red_add_f32x4(row + xs, r0[0], r0[1], r0[2], r0[3]);
-                    if (y1ok) red_add_f32x4(row + ys + xs, r1[0], r1[1], r1[2], r1[3]);
+                    if (y0ok) flush(row + xs, r0);
+                    if (y1ok) flush(row + ys + xs, r1);
                 }
 #pragma unroll
-                for (int k2 = 0; k2 < 4; ++k2) l0[k2] = l1[k2] = r0[k2] = r1[k2] = 0.f;
+                for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) l0[j][k2] = l1[j][k2] = r0[j][k2] = r1[j][k2] = 0.f;
                 lt = rt = false;
             }
         }
     }
 }
 
-template <typename VT, int D, bool FUSED>
-int run_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
-            const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, int ref_dim, cudaStream_t st)
+template <typename VT, int D, bool FUSED, int CPL, int MINB>
+int launch_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
+               const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, int ref_dim, cudaStream_t st)
 {
-    // chunk size / register cap / where the chunk's grad_out rows live were swept on B200
-    // (profiles/r01b_sweep_binned_flavours*.jsonl): 256 queries at 80 registers (3 CTAs/SM) with grad_out re-read
-    // through L1/L2 in phase C wins -- parking the rows in shared memory (+32 KB per CTA) shrinks L1 to ~28 KB and
-    // costs 3 %; 64 registers (4 CTAs/SM), 128 registers (2 CTAs/SM) and 128/160/320/512-query chunks are 1-10 % slower
-    using C = BinCfg<D>;
-    auto kern = bwd_bin_kernel<VT, D, FUSED>;
+    using C = BinCfg<D, 0, CPL>;
+    auto kern = bwd_bin_kernel<VT, D, FUSED, 0, MINB, CPL>;
     static bool prepared[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -445,6 +459,38 @@ int run_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const 
                                                         (float *)gl, (float *)ga, d, (const float *)ref, ref_dim, kBinSamples);
     count_launch();
     return (int)cudaGetLastError();
+}
+
+// D = 64 takes 8 channels per lane (8-lane groups, 256-query chunks like D = 32) when `value` is aligned to 8 elements
+// and, fused, the L*P logits fit kMaxBatches batches of 8 lanes
+template <typename VT, int D, bool FUSED>
+bool bin_wide(const void *value, const Dims &d)
+{
+    return D == 64 && tuning().bwd_pipe != 4 && reinterpret_cast<uintptr_t>(value) % (8 * sizeof(VT)) == 0 &&
+           (!FUSED || d.L * d.P <= kMaxBatches * (D / 8));
+}
+
+template <typename VT, int D, bool FUSED>
+int run_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc, const void *attn,
+            const void *grad_out, void *gv, void *gl, void *ga, const Dims &d, const void *ref, int ref_dim, cudaStream_t st)
+{
+    // chunk size / register cap / where the chunk's grad_out rows live were swept on B200
+    // (profiles/r01b_sweep_binned_flavours*.jsonl): 256 queries at 80 registers (3 CTAs/SM) with grad_out re-read
+    // through L1/L2 in phase C wins -- parking the rows in shared memory (+32 KB per CTA) shrinks L1 to ~28 KB and
+    // costs 3 %; 64 registers (4 CTAs/SM), 128 registers (2 CTAs/SM) and 128/160/320/512-query chunks are 1-10 % slower
+    if constexpr (D == 64) {
+        if (bin_wide<VT, D, FUSED>(value, d)) {
+            // profiles/r02_bwd_bin_d64_interleaved.jsonl (configs[1] shape with 4 heads of 64, timed alternately): fp32
+            // 1.47 ms at 2 CTAs/SM (128 registers, no spills) against 1.57 at 3 CTAs/SM (80 registers, 96 B spilled) and
+            // 1.58 for the 4-channel flavour; bf16 1.48 (3 CTAs/SM) against 1.65
+#ifdef MSDA_AB
+            if (tuning().bwd_pipe == 83)
+                return launch_bin<VT, D, FUSED, 8, 3>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
+#endif
+            return launch_bin<VT, D, FUSED, 8, 2>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
+        }
+    }
+    return launch_bin<VT, D, FUSED, 4, 3>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
 }
 
 template <typename VT, bool FUSED>
@@ -473,7 +519,7 @@ bool binned_backward_applies(const Dims &d, DType dt, bool vec_ok)
     // (profiles/r02_binned_crossover.jsonl, r02_kernel_family_table.jsonl) the binned kernel wins from ~2560 work items
     // (KITTI batch 8: 0.75 vs 0.78 ms; batch 16: 1.43 vs 1.54; Waymo batch 4: 2.01 vs 2.09), is level around 1300-2000
     // and loses below (KITTI batch 2: 0.26 vs 0.21 ms; KITTI-360 / 640x960 batch 4: 0.47 vs 0.43 ms).
-    const long chunk = d.D <= 32 ? 256 : 128;
+    const long chunk = 256;                          // queries per CTA (D = 64 without 32-byte aligned values: 128)
     return v == -1 && d.Lq >= kBinMinQueries && (long)d.N * d.M * ((d.Lq + chunk - 1) / chunk) >= 2560;
 }
 

@@ -349,8 +349,11 @@ def _tile_vs_oracle_and_record(msda, case_inputs, dtype, label, variants=(12, 20
         L.set_tuning("fwd_variant", variants[0]); L.set_tuning("bwd_variant", variants[1])
         check_against_oracle(msda, value, sh, lsi, loc, attn, grad_out, dtype, label=label)
         b = run_ours(msda, value.to(dtype), sh, lsi, loc.to(ct), attn.to(ct), grad_out.to(dtype))
-        # the 4-channel-per-lane record backward: the same partial sums in the same order as the binned / tile kernels
-        L.set_tuning("fwd_variant", 11); L.set_tuning("bwd_variant", 11); L.set_tuning("bwd_pipe", 4)
+        # the record backward with the same lane layout: the same partial sums in the same order (the binned kernel takes
+        # 8 channels per lane at D = 64 like the record kernel, the tile kernels always 4)
+        L.set_tuning("fwd_variant", 11); L.set_tuning("bwd_variant", 11)
+        if variants[1] == 20:
+            L.set_tuning("bwd_pipe", 4)
         a = run_ours(msda, value.to(dtype), sh, lsi, loc.to(ct), attn.to(ct), grad_out.to(dtype))
     finally:
         L.set_tuning("fwd_variant", -1); L.set_tuning("bwd_variant", -1); L.set_tuning("bwd_pipe", -1)
