@@ -297,6 +297,8 @@ def run_ours(args, wl):
     # sustained figure: the timed region above lasts tens of milliseconds at the driver's K; this block runs
     # `--sustain-steps` more steps back to back (one event pair, >= 0.2 s) so that a power-capped clock shows
     barrier()
+    for _ in range(3):                      # the GPU sat idle while rank 0 stopped the clock sampler: not part of "sustained"
+        keep = step_device()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
     for _ in range(args.sustain_steps):
