@@ -42,7 +42,8 @@ __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const fl
     using V = VecN<VT, CPL>;
     // LOADH_ = gather policy (Vec4 / VecN::gather) + 16 * stream-policy override (0: by lane-group size, see
     // ld_stream2 in msda_records.cuh; k > 0 forces policy k - 1)
-    constexpr int LOADH = LOADH_ % 16, SP = (LOADH_ / 16) ? LOADH_ / 16 - 1 : stream_policy<G>();
+    constexpr int LOADH = LOADH_ % 16, SP = ((LOADH_ / 16) % 4) ? (LOADH_ / 16) % 4 - 1 : stream_policy<G>();
+    constexpr bool CHAIN = LOADH_ >= 64;            // A/B: acc = fma(w, v, acc) four times instead of acc += (sum of 4)
     const int LP = d.L * d.P;
     const long qm = ((long)n * d.Lq + q) * d.M + m;
     const VT *vimg = value + ((long)n * d.S * d.M + m) * D + gl * CPL;
@@ -89,8 +90,16 @@ __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const fl
                         V::template gather<LOADH>(vimg + off.z, v10);
                         V::template gather<LOADH>(vimg + off.w, v11);
 #pragma unroll
-                        for (int c = 0; c < CPL; ++c)
-                            acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
+                        for (int c = 0; c < CPL; ++c) {
+                            if constexpr (CHAIN) {
+                                acc[c] = __fmaf_rn(wa.x, v00[c], acc[c]);
+                                acc[c] = __fmaf_rn(wa.y, v01[c], acc[c]);
+                                acc[c] = __fmaf_rn(wa.z, v10[c], acc[c]);
+                                acc[c] = __fmaf_rn(wa.w, v11[c], acc[c]);
+                            } else {
+                                acc[c] += wa.x * v00[c] + wa.y * v01[c] + wa.z * v10[c] + wa.w * v11[c];
+                            }
+                        }
                     }
                 }
                 __syncwarp();
@@ -349,6 +358,7 @@ int run_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const fl
             }
             if (tuning().fwd_pipe == 31) return MSDA_FWD_REC(8, 4, 16 + 1, false);       // A/B: evict-first streams
             if (tuning().fwd_pipe == 33) return MSDA_FWD_REC(8, 4, 48 + 1, false);       // A/B: evict-first streams, L2::128B hint
+            if (tuning().fwd_pipe == 40) return MSDA_FWD_REC(8, 4, 64 + 1, false);       // A/B: chained FMAs
             if (tuning().fwd_pipe == 27) return MSDA_FWD_REC(8, 5, 1, false);   // A/B: 5 CTAs per SM (48 registers, spills)
         }
     }
