@@ -490,6 +490,11 @@ int run_bin(const void *value, const int64_t *shapes, const int64_t *lsi, const 
             return launch_bin<VT, D, FUSED, 8, 2>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
         }
     }
+#ifdef MSDA_AB
+    if constexpr (D == 32)                       // A/B: 2 CTAs/SM, 128 registers (the fused flavour spills ~100 B at 80)
+        if (tuning().bwd_pipe == 92)
+            return launch_bin<VT, D, FUSED, 4, 2>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
+#endif
     return launch_bin<VT, D, FUSED, 4, 3>(value, shapes, lsi, loc, attn, grad_out, gv, gl, ga, d, ref, ref_dim, st);
 }
 
