@@ -101,12 +101,12 @@ bwd_rec_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
         const bool has = w.valid && sidx < LP;
         if constexpr (FUSED) {
             const int l = has ? sidx / d.P : 0;
-            const SampleIn r = fetch_sample_fused<stream_policy<G>()>(has, loc, ref, ref_dim, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l,
+            const SampleIn r = fetch_sample_fused<stream_policy<G, VT>()>(has, loc, ref, ref_dim, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l,
                                                   d.P, aw[0]);
             aw[0] = aw[1]; aw[1] = aw[2]; aw[2] = aw[3];
             return r;
         } else {
-            return fetch_sample<stream_policy<G>()>(has, loc, attn, qm * LP + sidx);
+            return fetch_sample<stream_policy<G, VT>()>(has, loc, attn, qm * LP + sidx);
         }
     };
     SampleIn in = fetch(gl);

@@ -210,7 +210,7 @@ bwd_tile_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
                         float aw[kMaxBatches];
                         group_softmax<G>(attn, qm * LP, LP, gl, qvalid, aw);
                         const float a = batch == 0 ? aw[0] : (batch == 1 ? aw[1] : (batch == 2 ? aw[2] : aw[3]));
-                        in = fetch_sample_fused<stream_policy<G>()>(has, loc, ref, ref_dim, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l, d.P, a);
+                        in = fetch_sample_fused<stream_policy<G, VT>()>(has, loc, ref, ref_dim, qm * LP + sidx, (qm / d.M) * d.L + l, s_lv, l, d.P, a);
                     } else {
                         in = in_next;
                     }

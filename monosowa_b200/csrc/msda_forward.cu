@@ -42,7 +42,7 @@ __device__ __forceinline__ void fwd_group(const VT *__restrict__ value, const fl
     using V = VecN<VT, CPL>;
     // LOADH_ = gather policy (Vec4 / VecN::gather) + 16 * stream-policy override (0: by lane-group size, see
     // ld_stream2 in msda_records.cuh; k > 0 forces policy k - 1)
-    constexpr int LOADH = LOADH_ % 16, SP = ((LOADH_ / 16) % 4) ? (LOADH_ / 16) % 4 - 1 : stream_policy<G>();
+    constexpr int LOADH = LOADH_ % 16, SP = ((LOADH_ / 16) % 4) ? (LOADH_ / 16) % 4 - 1 : stream_policy<G, VT>();
     constexpr bool CHAIN = LOADH_ >= 64;            // A/B: acc = fma(w, v, acc) four times instead of acc += (sum of 4)
     const int LP = d.L * d.P;
     const long qm = ((long)n * d.Lq + q) * d.M + m;
@@ -304,9 +304,14 @@ int launch_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const
                const Dims &d, const float *ref, int ref_dim, cudaStream_t st)
 {
     constexpr int QPW = 32 / (D / CPL);
-    const long grid = grid_for(d, 1, QPW, 256);
+#ifdef MSDA_AB
+    const int order = tuning().fwd_pipe == 41 ? 0 : 1;      // A/B: a CTA's warps walk the heads of one query chunk
+#else
+    const int order = 1;
+#endif
+    const long grid = grid_for(d, order, QPW, 256);
     if (grid > 0x7fffffffL) return kUnsupported;
-    fwd_rec_kernel<VT, D, MINB, FUSED, LOADH, COMPACT, CPL><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, 1, ref, ref_dim);
+    fwd_rec_kernel<VT, D, MINB, FUSED, LOADH, COMPACT, CPL><<<(unsigned)grid, 256, 0, st>>>(value, shapes, lsi, loc, attn, out, d, order, ref, ref_dim);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -234,8 +234,10 @@ struct SampleIn {
 //   configs[1]: 572 MB of DRAM reads with SP = 0, 418 MB = the compulsory inputs with SP = 1, same run time;
 //   profiles/r02_fwd_dram_by_flavour.txt).
 // SP = 2: evict-first with an L2::128B prefetch hint (A/B: does not keep the line either, 574 MB).
-template <int G>
-__host__ __device__ constexpr int stream_policy() { return G < 8 ? 1 : 0; }
+// bf16 values keep SP = 0 whatever G is: there the evict-normal streams cost time instead (D = 32 forward at configs[1]:
+// 0.450 ms / 334 MB read against 0.431 ms / 529 MB -- the run time is what counts; profiles/r02_fwd_stream_policy_bf16.jsonl).
+template <int G, typename VT>
+__host__ __device__ constexpr int stream_policy() { return (G < 8 && sizeof(VT) == 4) ? 1 : 0; }
 
 template <int SP>
 __device__ __forceinline__ float2 ld_stream2(const float2 *p)
