@@ -317,8 +317,9 @@ int launch_rec(const VT *value, const int64_t *shapes, const int64_t *lsi, const
 }
 
 // Eight channels per lane (fp32: one 256-bit load per corner, bf16: one 128-bit load) when D allows at least four
-// lanes per (query, head): a record read costs the L1 data pipe 4 wavefronts per LDS.128 whatever the broadcast, so a
-// warp step that serves 32 / (D/8) samples instead of 32 / (D/4) halves the record share of the pipe.
+// lanes per (query, head): a broadcast LDS.128 costs the L1 data pipe ~2.5 wavefronts whether it serves 4 or 8 lane
+// groups (ncu), so a warp step that serves 32 / (D/8) samples instead of 32 / (D/4) halves the record share of the pipe
+// (23.5 M -> 12.9 M wavefronts per launch at configs[1]) and the number of gather requests.
 // The 256-bit load needs a 32-byte aligned base; rows are D * sizeof(VT) apart, a multiple of 32 B when D % 8 == 0.
 template <typename VT, int D, bool FUSED>
 bool wide_lanes(const VT *value, const Dims &d)
