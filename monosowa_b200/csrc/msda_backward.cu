@@ -364,7 +364,10 @@ int run_rec(const void *value, const int64_t *shapes, const int64_t *lsi, const 
         if (ok && tuning().bwd_pipe == 82) return MSDA_BWD_REC(8, 2);
         if (ok && tuning().bwd_pipe == 83) return MSDA_BWD_REC(8, 3);
 #endif
-        if (ok && D == 64 && tuning().bwd_pipe != 4) return MSDA_BWD_REC(8, 3);
+        if constexpr (D == 64) {                   // (D = 32 with 8 channels exists in the measurement build only)
+            if (ok && tuning().bwd_pipe != 4) return MSDA_BWD_REC(8, 3);
+        }
+        (void)ok;
     }
     constexpr int MINB = D <= 32 ? 3 : 1;          // 80 registers, 3 CTAs/SM (profiles/r01b_sweep_binned_flavours.jsonl)
     return MSDA_BWD_REC(4, MINB);
