@@ -454,6 +454,7 @@ def run_ours(args, wl):
         "config": workload_config(wl, world),
         "value_sustained": value_sustained, "ms_per_step_sustained": ms_sustained, "sustain_steps": args.sustain_steps,
         "frac_of_hbm_peak": value / world / peak,
+        "frac_of_nominal_hbm_peak": value / world / 8000.0,      # north_star's nominal 8 TB/s, for reference
         "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
         "fwd_GBps": ab["fwd"] / (fwd_ms * 1e-3) / 1e9, "bwd_GBps": ab["bwd"] / (bwd_ms * 1e-3) / 1e9,
         "algorithmic_bytes": {"fwd": ab["fwd"], "bwd": ab["bwd"], "gather_cache_level": ab["gather"]},
